@@ -1,0 +1,92 @@
+"""ctypes binding of libfcmf_b200.so (the C ABI declared in include/fcmf_b200.h).
+
+There is no CPU fallback and no PyTorch fallback: if the library is missing or a call fails, a RuntimeError is
+raised with the library's own message (fcmf_last_error)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfcmf_b200.so")
+
+F32, BF16 = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_TANH, EPI_DGELU = 0, 1, 2, 3
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", _vp), ("ld", _i64), ("rows", _i32), ("idx", _vp)]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [("q", Seg * 2), ("k", Seg * 2), ("v", Seg * 2),
+                ("mask_add", _vp), ("ld_mask", _i64), ("mask_div", _i32),
+                ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32)]
+
+
+# name -> argtypes (every entry point returns int); must list EVERY symbol include/fcmf_b200.h declares.
+PROTOTYPES = {
+    "fcmf_abi_version": [],
+    "fcmf_device_info": [C.POINTER(C.c_int)] * 3,
+    "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "fcmf_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
+    "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp],
+    "fcmf_mask_additive": [_vp, _i64, _vp, _i64, _i64, _vp],
+    "fcmf_gather_sum_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp],
+    "fcmf_dtanh": [_vp, _vp, _vp, _i64, C.c_int, _vp],
+    "fcmf_cast_matrix": [_vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp],
+    "fcmf_cast_to_f32": [_vp, _vp, _i64, C.c_int, _vp],
+    "fcmf_attn_fwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, C.c_int, _vp],
+    "fcmf_attn_bwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp],
+    "fcmf_box_geometry_fwd": [_vp, _vp, _vp, C.POINTER(_f32), _vp, _vp, _i64, _i32, _i32, _vp],
+    "fcmf_box_geometry_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
+    "fcmf_cls_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.c_int, _vp],
+    "fcmf_cls_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.c_int, _vp],
+}
+
+_lock = threading.Lock()
+_lib = None
+launches = 0          # number of C-ABI compute calls issued by this process (bench.py reports it)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises if it has not been built -- the product path never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built. Run `python -c 'import __graft_entry__ as g; "
+                f"g.build()'` (nvcc, sm_100a). There is no CPU or PyTorch fallback for the fusion path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)          # AttributeError => ABI mismatch, also loud
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        lib.fcmf_last_error.argtypes = []
+        lib.fcmf_last_error.restype = C.c_char_p
+        if lib.fcmf_abi_version() != 1:
+            raise RuntimeError(f"libfcmf_b200.so ABI version {lib.fcmf_abi_version()} != 1; rebuild")
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.fcmf_last_error().decode(errors='replace')}")
+    launches += 1
+
+
+def exported_symbols():
+    return list(PROTOTYPES) + ["fcmf_last_error"]

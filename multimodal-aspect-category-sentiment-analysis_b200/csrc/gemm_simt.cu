@@ -1,0 +1,190 @@
+// SIMT (CUDA-core, fp32-accumulate) GEMM: the fp32 parity engine and the checker for the tcgen05 engine.
+// Generic strides so one kernel serves forward (TN), input-gradient (TN on W^T) and weight-gradient (NT^T).
+#include "common.cuh"
+#include "gemm.h"
+
+namespace fcmf {
+
+constexpr int SBM = 64, SBN = 64, SBK = 16, STHREADS = 256;
+
+// C[m,n] = sum_k A(m,k) * B(n,k);  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(STHREADS)
+gemm_simt_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak,
+                 const TIn* __restrict__ B, int64_t sbn, int64_t sbk,
+                 const float* __restrict__ bias, TOut* __restrict__ D, int64_t ldd,
+                 TIn* __restrict__ aux, int64_t ldaux,
+                 int64_t M, int64_t N, int64_t K, int epi, int accumulate) {
+  __shared__ float As[SBK][SBM + 4];
+  __shared__ float Bs[SBK][SBN + 4];
+  const int t = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * SBM, n0 = (int64_t)blockIdx.x * SBN;
+  const bool a_kcontig = (sak == 1), b_kcontig = (sbk == 1);
+  // loader coordinates: 4 elements per thread per operand
+  const int a_r = a_kcontig ? (t >> 2) : ((t & 15) << 2);
+  const int a_k = a_kcontig ? ((t & 3) << 2) : (t >> 4);
+  const int b_r = b_kcontig ? (t >> 2) : ((t & 15) << 2);
+  const int b_k = b_kcontig ? ((t & 3) << 2) : (t >> 4);
+  const int ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = 0; k0 < K; k0 += SBK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = a_kcontig ? a_r : a_r + e, kk = a_kcontig ? a_k + e : a_k;
+      const int64_t m = m0 + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? to_f(A[m * sam + k * sak]) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = b_kcontig ? b_r : b_r + e, kk = b_kcontig ? b_k + e : b_k;
+      const int64_t n = n0 + r, k = k0 + kk;
+      Bs[kk][r] = (n < N && k < K) ? to_f(B[n * sbn + k * sbk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (epi == FCMF_EPI_GELU) {
+        if (aux) aux[m * ldaux + n] = from_f<TIn>(v);
+        v = gelu_erf(v);
+      } else if (epi == FCMF_EPI_TANH) {
+        v = tanhf(v);
+      } else if (epi == FCMF_EPI_DGELU) {
+        v *= gelu_erf_grad(to_f(aux[m * ldaux + n]));
+      }
+      TOut* o = D + m * ldd + n;
+      if (accumulate) v += to_f(*o);
+      *o = from_f<TOut>(v);
+    }
+  }
+}
+
+// db[n] (+)= sum_m dY[m, n]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, float* __restrict__ db, int64_t M, int64_t N,
+                              int64_t rows_per_block) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t m_lo = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t m_hi = m_lo + rows_per_block < M ? m_lo + rows_per_block : M;
+  float s = 0.f;
+  for (int64_t m = m_lo; m < m_hi; ++m) s += to_f(dY[m * ld + n]);
+  atomicAdd(db + n, s);
+}
+
+template <typename T>
+int colsum_launch(const T* dY, int64_t ld, float* db, int64_t M, int64_t N, int accumulate, cudaStream_t st) {
+  if (!accumulate) FCMF_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
+  if (M == 0) return 0;
+  int64_t want_blocks_y = (4LL * sm_count() * 128 + N - 1) / N;       // ~4 waves of 128-thread blocks
+  if (want_blocks_y < 1) want_blocks_y = 1;
+  int64_t rows = (M + want_blocks_y - 1) / want_blocks_y;
+  if (rows < 32) rows = 32;
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + rows - 1) / rows));
+  colsum_kernel<T><<<grid, 128, 0, st>>>(dY, ld, db, M, N, rows);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+int colsum(const void* dY, int64_t ld, float* db, int64_t M, int64_t N, int accumulate, int dtype, cudaStream_t st) {
+  return dtype == FCMF_BF16 ? colsum_launch((const bf16*)dY, ld, db, M, N, accumulate, st)
+                            : colsum_launch((const float*)dY, ld, db, M, N, accumulate, st);
+}
+
+template <typename T>
+static int simt_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, void* D, int64_t ldd,
+                   void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi, cudaStream_t st) {
+  dim3 grid((unsigned)((N + SBN - 1) / SBN), (unsigned)((M + SBM - 1) / SBM));
+  gemm_simt_kernel<T, T><<<grid, STHREADS, 0, st>>>((const T*)A, lda, 1, (const T*)B, ldb, 1, bias, (T*)D, ldd,
+                                                    (T*)aux, ldaux, M, N, K, epi, 0);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_simt_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, void* D, int64_t ldd,
+                 void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi, int dtype, cudaStream_t st) {
+  if (M == 0 || N == 0) return 0;
+  return dtype == FCMF_BF16 ? simt_tn<bf16>(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, st)
+                            : simt_tn<float>(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, st);
+}
+
+template <typename T>
+static int simt_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N,
+                      int64_t K, int accumulate, cudaStream_t st) {
+  // dW[n,k] = sum_m dY[m,n] X[m,k]: "A"(n,m) = dY[m*lddy + n], "B"(k,m) = X[m*ldx + k]; reduction length M.
+  dim3 grid((unsigned)((K + SBN - 1) / SBN), (unsigned)((N + SBM - 1) / SBM));
+  gemm_simt_kernel<T, float><<<grid, STHREADS, 0, st>>>((const T*)dY, 1, lddy, (const T*)X, 1, ldx, nullptr, dW, K,
+                                                        nullptr, 0, N, K, M, FCMF_EPI_NONE, accumulate);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_simt_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N,
+                    int64_t K, int accumulate, int dtype, cudaStream_t st) {
+  if (N == 0 || K == 0) return 0;
+  return dtype == FCMF_BF16 ? simt_wgrad<bf16>(dY, lddy, X, ldx, dW, M, N, K, accumulate, st)
+                            : simt_wgrad<float>(dY, lddy, X, ldx, dW, M, N, K, accumulate, st);
+}
+
+}  // namespace fcmf
+
+using namespace fcmf;
+
+extern "C" int fcmf_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, void* D,
+                            int64_t ldd, void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi,
+                            int dtype, int engine, void* stream) {
+  FCMF_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_tn: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  FCMF_CHECK_ARG(dtype == FCMF_F32 || dtype == FCMF_BF16, "gemm_tn: bad dtype %d", dtype);
+  FCMF_CHECK_ARG(epi >= FCMF_EPI_NONE && epi <= FCMF_EPI_DGELU, "gemm_tn: bad epilogue %d", epi);
+  FCMF_CHECK_ARG(epi != FCMF_EPI_DGELU || aux != nullptr, "gemm_tn: EPI_DGELU needs aux");
+  FCMF_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "gemm_tn: leading dimension too small");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const bool tc_ok = dtype == FCMF_BF16 && gemm_tc_supported_tn(M, N, K, lda, ldb, ldd, ldaux, A, B, D, aux);
+  if (engine == FCMF_ENGINE_TCGEN05 && !tc_ok)
+    return fail(FCMF_ERR_UNSUPPORTED, "gemm_tn: tcgen05 engine cannot run M=%lld N=%lld K=%lld dtype=%d",
+                (long long)M, (long long)N, (long long)K, dtype);
+  if (engine == FCMF_ENGINE_TCGEN05 || (engine == FCMF_ENGINE_AUTO && tc_ok))
+    return gemm_tc_tn(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, st);
+  return gemm_simt_tn(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, dtype, st);
+}
+
+extern "C" int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, float* db,
+                               int64_t M, int64_t N, int64_t K, int accumulate, int dtype, int engine, void* stream) {
+  FCMF_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_wgrad: bad shape");
+  FCMF_CHECK_ARG(dtype == FCMF_F32 || dtype == FCMF_BF16, "gemm_wgrad: bad dtype %d", dtype);
+  FCMF_CHECK_ARG(lddy >= N && ldx >= K, "gemm_wgrad: leading dimension too small");
+  cudaStream_t st = as_stream(stream);
+  if (db) { int r = colsum(dY, lddy, db, M, N, accumulate, dtype, st); if (r) return r; }
+  const bool tc_ok = dtype == FCMF_BF16 && gemm_tc_supported_wgrad(M, N, K, lddy, ldx, dY, X);
+  if (engine == FCMF_ENGINE_TCGEN05 && !tc_ok)
+    return fail(FCMF_ERR_UNSUPPORTED, "gemm_wgrad: tcgen05 engine cannot run M=%lld N=%lld K=%lld dtype=%d",
+                (long long)M, (long long)N, (long long)K, dtype);
+  if (engine == FCMF_ENGINE_TCGEN05 || (engine == FCMF_ENGINE_AUTO && tc_ok))
+    return gemm_tc_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, st);
+  return gemm_simt_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, dtype, st);
+}

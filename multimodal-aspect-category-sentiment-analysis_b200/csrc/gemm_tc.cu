@@ -1,0 +1,462 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   * persistent, warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and
+//     TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each);
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a kStages-deep shared-memory ring,
+//     consumed by tcgen05.mma.cta_group::1.kind::f16 straight from shared memory through matrix descriptors;
+//   * the 128 x BN fp32 accumulator lives in TMEM, double-buffered so the epilogue of tile i overlaps the
+//     main loop of tile i+1; epilogue = tcgen05.ld -> bias / erf-GELU / tanh / dGELU -> global;
+//   * both operand majors: K-major (forward and input-gradient GEMMs) and MN-major (weight-gradient GEMM,
+//     where the reduction runs over the rows of two row-major activation matrices), split along the
+//     reduction with fp32 atomics for the weight gradient.
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables
+// (same bit layout as cute::UMMA::SmemDescriptor / InstrDescriptor).
+#include "common.cuh"
+#include "gemm.h"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace fcmf {
+
+// ------------------------------------------------------------------------------------------- tile configuration
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_UMMA_K = 16;
+constexpr int TC_THREADS = 192;                 // 6 warps
+constexpr int TC_EPI_WARP0 = 2;                 // warps 2..5
+constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024; // ring + barriers, leaves room under the 227 KB limit
+
+template <int BN> struct TcCfg {
+  static constexpr int kStageA = TC_BM * TC_BK * 2;                 // 16 KB
+  static constexpr int kStageB = BN * TC_BK * 2;                    // 16 / 32 KB
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (int)(TC_SMEM_BUDGET / kStageBytes) > 8 ? 8 : (int)(TC_SMEM_BUDGET / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (256 / 512)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 6000000000LL) {   // ~3-4 s
+      printf("fcmf gemm_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_out, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, version 1). Offsets are in bytes; >>4 encodes 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // [0,14)  start address
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride byte offset
+  d |= (uint64_t)1 << 46;                                  // [46,48) descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                  // [61,64) SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, M x N tile, operand majors.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+struct TcParams {
+  // logical GEMM: D[Mg, Ng] = sum_k A(m,k) B(n,k), k < Kg
+  int64_t Mg, Ng, Kg;
+  int m_tiles, n_tiles, k_blocks, splits;      // work unit = (tile, split)
+  // epilogue
+  const float* bias;
+  bf16* D; int64_t ldd;
+  bf16* aux; int64_t ldaux;
+  float* Df; int64_t lddf;                     // fp32 output (weight gradient)
+  int epi;
+  int f32_mode;                                // 0 = bf16 epilogue, 1 = fp32 store, 2 = fp32 atomic add
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;          // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;
+  const int kb_per_split = (P.k_blocks + P.splits - 1) / P.splits;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = (int)(u % P.splits);
+        const int64_t tile = u / P.splits;
+        const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(P.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kStageA;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);          // box [64 k][128 rows]
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; ++c)                                           // box [64 m][64 k-rows]
+              tma_load_2d(sa + c * (TC_BK * 128), &tmA, &full_bar[stage], m_blk * TC_BM + c * 64, kb * TC_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * TC_BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (TC_BK * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * TC_BK);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // K-major: 8-row groups are 1024 B apart (SBO); LBO unused (encoded 1).  MN-major: 64-element column
+      // blocks are BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t a_lbo = A_MN ? TC_BK * 128 : 16, b_lbo = B_MN ? TC_BK * 128 : 16;
+      constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
+      constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int split = (int)(u % P.splits);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(P.k_blocks, kb0 + kb_per_split);
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                  // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);                      // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps, one lane quarter each)
+    const int quarter = warp & 3;
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      const int split = (int)(u % P.splits);
+      const int64_t tile = u / P.splits;
+      const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
+      const int kb0 = split * kb_per_split;
+      const bool has_work = kb0 < P.k_blocks;              // an empty split contributes nothing
+      const uint32_t buf = it & 1, use = it >> 1;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_blk * TC_BM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
+        if (m < P.Mg && n0 < P.Ng && has_work) {
+          if (P.f32_mode == 0) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const int ncols = (int)min((int64_t)32, P.Ng - n0);       // multiple of 8 (checked on the host)
+            if (P.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(P.bias + n0 + j);
+            }
+            if (P.epi == FCMF_EPI_GELU) {
+              if (P.aux) {
+                bf16* ap = P.aux + m * P.ldaux + n0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+                  uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+                  *reinterpret_cast<uint4*>(ap + g * 8) = w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (P.epi == FCMF_EPI_TANH) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            } else if (P.epi == FCMF_EPI_DGELU) {
+              const bf16* ap = P.aux + m * P.ldaux + n0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+                const uint4 w = *reinterpret_cast<const uint4*>(ap + g * 8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(h[j]);
+                  v[g * 8 + 2 * j] *= gelu_erf_grad(f.x);
+                  v[g * 8 + 2 * j + 1] *= gelu_erf_grad(f.y);
+                }
+              }
+            }
+            bf16* dp = P.D + m * P.ldd + n0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+              uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(dp + g * 8) = w;
+            }
+          } else {
+            float* dp = P.Df + m * P.lddf + n0;
+            const int ncols = (int)min((int64_t)32, P.Ng - n0);
+            if (P.f32_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_cols (inner), box_rows].
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(FCMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCMF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+                (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows);
+  return 0;
+}
+
+static bool ok16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool gemm_tc_supported_tn(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int64_t ldaux,
+                          const void* A, const void* B, const void* D, const void* aux) {
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31)) return false;
+  if ((N % 8) || (K % 8) || (lda % 8) || (ldb % 8) || (ldd % 8) || (aux && (ldaux % 8))) return false;
+  return ok16(A) && ok16(B) && ok16(D) && ok16(aux);
+}
+
+bool gemm_tc_supported_wgrad(int64_t M, int64_t N, int64_t K, int64_t lddy, int64_t ldx, const void* dY, const void* X) {
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31)) return false;
+  if ((N % 8) || (K % 8) || (lddy % 8) || (ldx % 8)) return false;
+  return ok16(dY) && ok16(X);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set[64] = {false};                       // per instantiation, per device
+  int dev = 0;
+  FCMF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    FCMF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;
+  const int grid = (int)(units < sm_count() ? units : sm_count());
+  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, P);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, void* D, int64_t ldd,
+               void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi, cudaStream_t st) {
+  TcParams P{};
+  P.Mg = M; P.Ng = N; P.Kg = K;
+  P.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  P.k_blocks = (int)((K + TC_BK - 1) / TC_BK);
+  P.splits = 1;
+  P.bias = bias; P.D = (bf16*)D; P.ldd = ldd; P.aux = (bf16*)aux; P.ldaux = ldaux; P.epi = epi; P.f32_mode = 0;
+  // 256-wide tiles unless that leaves SMs idle
+  const int64_t tiles256 = (int64_t)P.m_tiles * ((N + 255) / 256);
+  const bool wide = (N % 256 == 0 || N > 1024) && tiles256 >= sm_count();
+  CUtensorMap ta, tb;
+  if (int r = make_map(&ta, A, M, K, lda, TC_BK, TC_BM)) return r;
+  if (wide) {
+    P.n_tiles = (int)((N + 255) / 256);
+    if (int r = make_map(&tb, B, N, K, ldb, TC_BK, 256)) return r;
+    return launch<256, false, false>(ta, tb, P, st);
+  }
+  P.n_tiles = (int)((N + 127) / 128);
+  if (int r = make_map(&tb, B, N, K, ldb, TC_BK, 128)) return r;
+  return launch<128, false, false>(ta, tb, P, st);
+}
+
+int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N, int64_t K,
+                  int accumulate, cudaStream_t st) {
+  // dW[N,K] = sum_m dY[m,n] X[m,k]: GEMM rows = N (out features), cols = K (in features), reduction = M rows.
+  TcParams P{};
+  P.Mg = N; P.Ng = K; P.Kg = M;
+  P.m_tiles = (int)((N + TC_BM - 1) / TC_BM);
+  P.k_blocks = (int)((M + TC_BK - 1) / TC_BK);
+  const bool wide = (K % 256 == 0);
+  const int bn = wide ? 256 : 128;
+  P.n_tiles = (int)((K + bn - 1) / bn);
+  const int64_t tiles = (int64_t)P.m_tiles * P.n_tiles;
+  int splits = (int)((sm_count() + tiles - 1) / tiles);
+  if (splits > P.k_blocks) splits = P.k_blocks;
+  if (splits < 1) splits = 1;
+  // make every split non-empty
+  while (splits > 1 && (int64_t)(splits - 1) * ((P.k_blocks + splits - 1) / splits) >= P.k_blocks) --splits;
+  P.splits = splits;
+  P.Df = dW; P.lddf = K; P.epi = FCMF_EPI_NONE;
+  P.f32_mode = (splits == 1 && !accumulate) ? 1 : 2;
+  if (P.f32_mode == 2 && !accumulate) FCMF_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st));
+  CUtensorMap ta, tb;
+  if (int r = make_map(&ta, dY, M, N, lddy, 64, TC_BK)) return r;       // box [64 features][64 rows]
+  if (int r = make_map(&tb, X, M, K, ldx, 64, TC_BK)) return r;
+  return wide ? launch<256, true, true>(ta, tb, P, st) : launch<128, true, true>(ta, tb, P, st);
+}
+
+}  // namespace fcmf

@@ -1,0 +1,362 @@
+// HBM-bound row-wise kernels: residual + TF-style LayerNorm (fwd/bwd), additive masks, row gather/sum,
+// tanh backward and weight staging casts. One warp owns one row; 16-byte vector accesses; row kept in
+// registers between the statistics pass and the normalisation pass (one HBM read per operand).
+#include "common.cuh"
+
+namespace fcmf {
+
+constexpr int LN_WARPS = 4;
+
+// ------------------------------------------------------------------------------------------- LayerNorm fwd
+template <typename T, int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t* __restrict__ res_idx,
+              const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
+              float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H, float eps) {
+  constexpr int N = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T* xr = x + row * H;
+  const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
+  float v[VPL][N];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * N;
+    if (c < H) {
+      Vec16<T> a; a.load(xr + c);
+      if (rr) { Vec16<T> b; b.load(rr + c);
+#pragma unroll
+        for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
+#pragma unroll
+      for (int j = 0; j < N; ++j) { v[i][j] = a.v[j]; sum += a.v[j]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mu = warp_sum(sum) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * N;
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) { const float d = v[i][j] - mu; sq += d * d; }
+    }
+  }
+  const float var = warp_sum(sq) / (float)H;          // biased variance, mm_modeling.py:169
+  const float rs = 1.0f / sqrtf(var + eps);           // eps inside the sqrt, mm_modeling.py:170
+  if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+  T* yr = y + row * H;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * N;
+    if (c < H) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; ++j) o.v[j] = gamma[c + j] * ((v[i][j] - mu) * rs) + beta[c + j];
+      o.store(yr + c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm bwd
+template <typename T, int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* __restrict__ x, const T* __restrict__ res,
+              const int32_t* __restrict__ res_idx, const float* __restrict__ gamma,
+              const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H) {
+  constexpr int N = Vec16<T>::N;
+  extern __shared__ float red[];                      // [LN_WARPS][2][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float g[VPL][N], dg[VPL][N], db[VPL][N];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * N;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { g[i][j] = (c < H) ? gamma[c + j] : 0.f; dg[i][j] = 0.f; db[i][j] = 0.f; }
+  }
+  const int64_t stride = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += stride) {
+    const T* xr = x + row * H;
+    const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
+    const T* dyr = dy + row * H;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL][N], gy[VPL][N];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * N;
+      if (c < H) {
+        Vec16<T> a, d; a.load(xr + c); d.load(dyr + c);
+        if (dy_add) { Vec16<T> e; e.load(dy_add + row * H + c);
+#pragma unroll
+          for (int j = 0; j < N; ++j) d.v[j] += e.v[j]; }
+        if (rr) { Vec16<T> b; b.load(rr + c);
+#pragma unroll
+          for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          xh[i][j] = (a.v[j] - mu) * rs;
+          gy[i][j] = d.v[j] * g[i][j];
+          s1 += gy[i][j];
+          s2 += gy[i][j] * xh[i][j];
+          dg[i][j] += d.v[j] * xh[i][j];
+          db[i][j] += d.v[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { xh[i][j] = 0.f; gy[i][j] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    T* dsr = ds + row * H;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * N;
+      if (c < H) {
+        Vec16<T> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j) o.v[j] = rs * (gy[i][j] - s1 - xh[i][j] * s2);
+        o.store(dsr + c);
+      }
+    }
+  }
+  // block reduction of the column sums, then one atomic per column per block
+  float* my = red + (size_t)warp * 2 * H;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = (i * 32 + lane) * N;
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) { my[c + j] = dg[i][j]; my[H + c + j] = db[i][j]; }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) s += red[(size_t)w * 2 * H + c];
+    atomicAdd((c < H ? dgamma + c : dbeta + (c - H)), s);
+  }
+}
+
+template <typename T, int VPL>
+static int ln_fwd_launch(const void* x, const void* res, const int32_t* idx, const float* gamma, const float* beta,
+                         void* y, float* mean, float* rstd, int64_t M, int H, float eps, cudaStream_t st) {
+  const unsigned grid = (unsigned)((M + LN_WARPS - 1) / LN_WARPS);
+  ln_fwd_kernel<T, VPL><<<grid, LN_WARPS * 32, 0, st>>>((const T*)x, (const T*)res, idx, gamma, beta, (T*)y, mean,
+                                                         rstd, M, H, eps);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+template <typename T, int VPL>
+static int ln_bwd_launch(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* idx, const float* gamma,
+                         const float* mean, const float* rstd, void* ds, float* dgamma, float* dbeta, int64_t M, int H,
+                         cudaStream_t st) {
+  int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = sizeof(float) * LN_WARPS * 2 * H;
+  ln_bwd_kernel<T, VPL><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
+      (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, dgamma, dbeta, M, H);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+#define FCMF_LN_DISPATCH(T, fn, ...)                                          \
+  do {                                                                        \
+    const int per = 32 * Vec16<T>::N;                                         \
+    const int vpl = (H + per - 1) / per;                                      \
+    switch (vpl) {                                                            \
+      case 1: return fn<T, 1>(__VA_ARGS__);                                   \
+      case 2: return fn<T, 2>(__VA_ARGS__);                                   \
+      case 3: return fn<T, 3>(__VA_ARGS__);                                   \
+      case 4: return fn<T, 4>(__VA_ARGS__);                                   \
+      case 5: case 6: return fn<T, 6>(__VA_ARGS__);                           \
+      case 7: case 8: return fn<T, 8>(__VA_ARGS__);                           \
+      default: return fail(FCMF_ERR_UNSUPPORTED, "layernorm: H=%d too wide", H); \
+    }                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------- small kernels
+__global__ void mask_additive_kernel(const int64_t* __restrict__ mask, int64_t ld, float* __restrict__ add,
+                                     int64_t rows, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * n) return;
+  const int64_t r = i / n, j = i - r * n;
+  add[i] = (1.0f - (float)mask[r * ld + j]) * -10000.0f;     // fcmf_pretraining.py:56
+}
+
+template <typename T>
+__global__ void gather_sum_rows_kernel(const T* __restrict__ src, int64_t ldsrc, const int32_t* __restrict__ idx,
+                                       T* __restrict__ out, int64_t ldout, int64_t n_out, int G, int width,
+                                       int accumulate) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t o = blockIdx.x;
+  const int32_t* ix = idx + o * G;
+  for (int c = threadIdx.x * N; c < width; c += blockDim.x * N) {
+    float acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.f;
+    if (accumulate) { Vec16<T> a; a.load(out + o * ldout + c);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] = a.v[j]; }
+    for (int g = 0; g < G; ++g) {
+      const int32_t r = ix[g];
+      if (r < 0) continue;
+      Vec16<T> a; a.load(src + (int64_t)r * ldsrc + c);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] += a.v[j];
+    }
+    Vec16<T> w;
+#pragma unroll
+    for (int j = 0; j < N; ++j) w.v[j] = acc[j];
+    w.store(out + o * ldout + c);
+  }
+}
+
+template <typename T>
+__global__ void dtanh_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ out, int64_t n) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * N;
+  if (i + N <= n) {
+    Vec16<T> a, b, o; a.load(dy + i); b.load(y + i);
+#pragma unroll
+    for (int j = 0; j < N; ++j) o.v[j] = a.v[j] * (1.0f - b.v[j] * b.v[j]);
+    o.store(out + i);
+  } else {
+    for (int64_t k = i; k < n; ++k) { const float t = to_f(y[k]); out[k] = from_f<T>(to_f(dy[k]) * (1.0f - t * t)); }
+  }
+}
+
+template <typename T>
+__global__ void cast_matrix_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int transpose) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  if (!transpose) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) dst[(int64_t)r * cols + c] = from_f<T>(tile[i][threadIdx.x]);
+    }
+  } else {                                              // dst is [cols, rows]
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < rows && c < cols) dst[(int64_t)c * rows + r] = from_f<T>(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void cast_to_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = to_f(src[i]);
+}
+
+}  // namespace fcmf
+
+using namespace fcmf;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_idx, const float* gamma,
+                           const float* beta, void* y, float* mean, float* rstd, int64_t M, int64_t H64, float eps,
+                           int dtype, void* stream) {
+  const int H = (int)H64;
+  FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_fwd: bad shape");
+  FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_fwd: H=%d must be a multiple of the 16-byte vector", H);
+  FCMF_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)), "ln_fwd: pointers must be 16-byte aligned");
+  if (M == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, st);
+  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, st);
+  return fail(FCMF_ERR_ARG, "ln_fwd: bad dtype %d", dtype);
+}
+
+extern "C" int fcmf_ln_bwd(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* res_idx, const float* gamma,
+                           const float* mean, const float* rstd, void* ds, float* dgamma, float* dbeta, int64_t M,
+                           int64_t H64, int dtype, void* stream) {
+  const int H = (int)H64;
+  FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_bwd: bad shape");
+  FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_bwd: H=%d must be a multiple of the 16-byte vector", H);
+  FCMF_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(ds) && (!res || aligned16(res)) && (!dy_add || aligned16(dy_add)), "ln_bwd: alignment");
+  if (M == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dgamma, dbeta, M, H, st);
+  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dgamma, dbeta, M, H, st);
+  return fail(FCMF_ERR_ARG, "ln_bwd: bad dtype %d", dtype);
+}
+
+extern "C" int fcmf_mask_additive(const int64_t* mask, int64_t ldmask, float* add, int64_t rows, int64_t n, void* stream) {
+  FCMF_CHECK_ARG(rows >= 0 && n >= 0 && ldmask >= n, "mask_additive: bad shape");
+  if (rows * n == 0) return 0;
+  mask_additive_kernel<<<(unsigned)((rows * n + 255) / 256), 256, 0, as_stream(stream)>>>(mask, ldmask, add, rows, n);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int fcmf_gather_sum_rows(const void* src, int64_t ldsrc, const int32_t* idx, void* out, int64_t ldout,
+                                    int64_t n_out, int64_t G, int64_t width, int accumulate, int dtype, void* stream) {
+  FCMF_CHECK_ARG(n_out >= 0 && G > 0 && width > 0, "gather_sum_rows: bad shape");
+  const int vec = dtype == FCMF_BF16 ? 8 : 4;
+  FCMF_CHECK_ARG(width % vec == 0 && ldsrc % vec == 0 && ldout % vec == 0 && aligned16(src) && aligned16(out),
+                 "gather_sum_rows: width/ld must be multiples of %d elements and pointers 16-byte aligned", vec);
+  if (n_out == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  int threads = (int)((width / vec + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (dtype == FCMF_BF16)
+    gather_sum_rows_kernel<bf16><<<(unsigned)n_out, threads, 0, st>>>((const bf16*)src, ldsrc, idx, (bf16*)out, ldout, n_out, (int)G, (int)width, accumulate);
+  else if (dtype == FCMF_F32)
+    gather_sum_rows_kernel<float><<<(unsigned)n_out, threads, 0, st>>>((const float*)src, ldsrc, idx, (float*)out, ldout, n_out, (int)G, (int)width, accumulate);
+  else return fail(FCMF_ERR_ARG, "gather_sum_rows: bad dtype %d", dtype);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int fcmf_dtanh(const void* dy, const void* y, void* out, int64_t n, int dtype, void* stream) {
+  FCMF_CHECK_ARG(n >= 0, "dtanh: bad n");
+  FCMF_CHECK_ARG(aligned16(dy) && aligned16(y) && aligned16(out), "dtanh: alignment");
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int vec = dtype == FCMF_BF16 ? 8 : 4;
+  const unsigned grid = (unsigned)(((n + vec - 1) / vec + 255) / 256);
+  if (dtype == FCMF_BF16) dtanh_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, (bf16*)out, n);
+  else if (dtype == FCMF_F32) dtanh_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y, (float*)out, n);
+  else return fail(FCMF_ERR_ARG, "dtanh: bad dtype %d", dtype);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int fcmf_cast_matrix(const float* src, void* dst, int64_t rows, int64_t cols, int transpose, int dtype, void* stream) {
+  FCMF_CHECK_ARG(rows >= 0 && cols >= 0 && rows < (1LL << 31) && cols < (1LL << 31), "cast_matrix: bad shape");
+  if (rows * cols == 0) return 0;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == FCMF_BF16) cast_matrix_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, (int)rows, (int)cols, transpose);
+  else if (dtype == FCMF_F32) cast_matrix_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, (int)rows, (int)cols, transpose);
+  else return fail(FCMF_ERR_ARG, "cast_matrix: bad dtype %d", dtype);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int fcmf_cast_to_f32(const void* src, float* dst, int64_t n, int dtype, void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == FCMF_BF16) cast_to_f32_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, dst, n);
+  else if (dtype == FCMF_F32) cast_to_f32_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, n);
+  else return fail(FCMF_ERR_ARG, "cast_to_f32: bad dtype %d", dtype);
+  FCMF_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,50 @@
+// Error plumbing, device queries and the ABI version entry points.
+#include "common.cuh"
+#include <stdarg.h>
+#include <mutex>
+
+namespace fcmf {
+
+std::string& last_error_ref() {
+  static thread_local std::string msg;
+  return msg;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace fcmf
+
+extern "C" int fcmf_abi_version(void) { return FCMF_ABI_VERSION; }
+
+extern "C" const char* fcmf_last_error(void) { return fcmf::last_error_ref().c_str(); }
+
+extern "C" int fcmf_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  FCMF_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  FCMF_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+  if (sm) *sm = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return 0;
+}

@@ -1,0 +1,172 @@
+"""IAOG Seq2Seq decoder -- consumer of the fusion output (reference
+mm_modeling.py:35-132 ``Attention``, :558-613 decoder block, :615-666 ``IAOGDecoder``).
+
+Scope note: this is the first "next" row after the fusion hot path. The dense contractions (per-head projections
+folded into one GEMM, output projection, FFN, the vocabulary projection) and every LayerNorm already run on the
+fusion path's kernels; the small T x T / T x 15 score/softmax core still uses PyTorch ops and is the piece left
+to fold into ``folded_attention`` (it needs a causal-mask flag in the kernel).
+
+Contract kept from the reference (each looks odd but is what checkpoints were trained with):
+  * per-head weight tensors ``w_kx`` / ``w_qx`` of shape [heads, H, dh]; the projected KEYS are also the values;
+  * a 2-D mask argument means tril(q_len x k_len) on self- AND cross-attention; masked_fill(-1e4), not -inf;
+  * no dropout inside ``Attention``; ``dense.weight`` is tied to ``embedding.weight``;
+  * the per-block key/value cache in ``state[2]`` is written but never read by attention1.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .fcmf_framework import mm_modeling as M
+
+
+class Attention(nn.Module):
+    def __init__(self, embed_dim, hidden_dim=None, n_head=1, score_function="scaled_dot_product", dropout=0.1):
+        super().__init__()
+        if score_function != "scaled_dot_product":
+            raise NotImplementedError("the IAOG decoder only instantiates scaled_dot_product attention")
+        hidden_dim = hidden_dim or embed_dim // n_head
+        self.embed_dim, self.hidden_dim, self.n_head, self.score_function = embed_dim, hidden_dim, n_head, score_function
+        self.w_kx = nn.Parameter(torch.empty(n_head, embed_dim, hidden_dim))
+        self.w_qx = nn.Parameter(torch.empty(n_head, embed_dim, hidden_dim))
+        self.proj = nn.Linear(n_head * hidden_dim, embed_dim)
+        self.register_parameter("weight", None)
+        nn.init.xavier_uniform_(self.w_kx)
+        nn.init.xavier_uniform_(self.w_qx)
+        self.attention_weights = None
+
+    def _project(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+        """x [B,T,E] times per-head [nh,E,dh] as ONE GEMM against the [nh*dh, E] stacking -> [B, nh, T, dh]."""
+        B, T, E = x.shape
+        w2 = w.permute(0, 2, 1).reshape(self.n_head * self.hidden_dim, E)
+        y = Fn.linear(x.reshape(B * T, E), w2, None)
+        return y.view(B, T, self.n_head, self.hidden_dim).permute(0, 2, 1, 3)
+
+    def forward(self, k, q, memory_len=None):
+        if k.dim() == 2:
+            k = k.unsqueeze(1)
+        if q.dim() == 2:
+            q = q.unsqueeze(1)
+        B, k_len, q_len = k.size(0), k.size(1), q.size(1)
+        kx = self._project(k, self.w_kx).float()
+        qx = self._project(q, self.w_qx).float()
+        score = torch.matmul(qx, kx.transpose(-1, -2)) / math.sqrt(self.hidden_dim)        # [B,nh,q,k]
+        if memory_len is not None:
+            if isinstance(memory_len, (list, tuple)):
+                memory_len = torch.tensor(memory_len, device=k.device)
+            if memory_len.dim() == 1:
+                keep = torch.arange(k_len, device=k.device).unsqueeze(0) < memory_len.unsqueeze(1)
+                score = score.masked_fill(~keep.view(B, 1, 1, k_len), -1e4)
+            elif memory_len.dim() == 2:
+                keep = torch.tril(torch.ones(q_len, k_len, device=k.device, dtype=torch.bool))
+                score = score.masked_fill(~keep, -1e4)
+        prob = torch.softmax(score, dim=-1)
+        # reference layout of the stored weights: [nh*B, q, k], head-major
+        self.attention_weights = prob.permute(1, 0, 2, 3).reshape(self.n_head * B, q_len, k_len)
+        out = torch.matmul(prob, kx).permute(0, 2, 1, 3).reshape(B * q_len, self.n_head * self.hidden_dim)
+        out = Fn.linear(out.to(k.dtype), self.proj.weight, self.proj.bias)
+        return out.view(B, q_len, self.embed_dim), self.attention_weights
+
+
+class PositionWiseFFN(nn.Module):
+    def __init__(self, ffn_num_hiddens, ffn_num_outputs):
+        super().__init__()
+        self.dense1 = nn.Linear(M.HIDDEN_SIZE, ffn_num_hiddens)
+        self.dense2 = nn.Linear(ffn_num_hiddens, ffn_num_outputs)
+
+    def forward(self, x):
+        shape = x.shape
+        h = M._GeluLinear.apply(x.reshape(-1, shape[-1]), self.dense1.weight, self.dense1.bias)
+        return Fn.linear(h, self.dense2.weight, self.dense2.bias).view(*shape[:-1], -1)
+
+
+class AddNorm(nn.Module):
+    def __init__(self, norm_shape, dropout):
+        super().__init__()
+        self.dropout_p = dropout
+        self.ln = M.FCMFLayerNorm(norm_shape)
+
+    def forward(self, X, Y):
+        shape = X.shape
+        return M._ResidualLayerNorm.apply(Y.reshape(-1, shape[-1]).contiguous(), X.reshape(-1, shape[-1]).contiguous(),
+                                          self.ln.weight, self.ln.bias, self.ln.variance_epsilon).view(shape)
+
+
+class TransformerDecoderBlock(nn.Module):
+    def __init__(self, i):
+        super().__init__()
+        self.i = i
+        H, nh = M.HIDDEN_SIZE, M.NUM_ATTENTION_HEADS
+        self.attention1 = Attention(H, H // nh, nh, "scaled_dot_product", M.ATTENTION_PROBS_DROPOUT_PROB)
+        self.addnorm1 = AddNorm(H, M.ATTENTION_PROBS_DROPOUT_PROB)
+        self.attention2 = Attention(H, H // nh, nh, "scaled_dot_product", M.ATTENTION_PROBS_DROPOUT_PROB)
+        self.addnorm2 = AddNorm(H, M.ATTENTION_PROBS_DROPOUT_PROB)
+        self.ffn = PositionWiseFFN(H, H)
+        self.add_norm3 = AddNorm(H, M.ATTENTION_PROBS_DROPOUT_PROB)
+
+    def forward(self, X, state, enc_attention_mask=None, is_train=True):
+        enc_outputs, enc_valid_lens = state[0], state[1]
+        if state[2][self.i] is not None:                         # written, never read by attention1 (reference :588-601)
+            state[2][self.i] = torch.cat((state[2][self.i], X), dim=1)
+        dec_valid_lens = None
+        if is_train:
+            B, T, _ = X.shape
+            dec_valid_lens = torch.arange(1, T + 1, device=X.device).repeat(B, 1)
+        X2, _ = self.attention1(X, X, dec_valid_lens)
+        Y = self.addnorm1(X, X2)
+        cross_mask = enc_attention_mask if enc_attention_mask is not None else enc_valid_lens
+        Y2, _ = self.attention2(enc_outputs.to(Y.dtype), Y, cross_mask)
+        Z = self.addnorm2(Y, Y2)
+        return self.add_norm3(Z, self.ffn(Z)), state
+
+
+class PositionalEncoding(nn.Module):
+    def __init__(self):
+        super().__init__()
+        H, n = M.HIDDEN_SIZE, M.MAX_POSITION_EMBEDDINGS
+        P = torch.zeros((1, n, H))
+        X = torch.arange(n, dtype=torch.float32).reshape(-1, 1) / torch.pow(
+            10000, torch.arange(0, H, 2, dtype=torch.float32) / H)
+        P[:, :, 0::2] = torch.sin(X)
+        P[:, :, 1::2] = torch.cos(X)
+        self.register_buffer("P", P)
+
+    def forward(self, X):
+        return X + self.P[:, :X.size(1), :].to(device=X.device).type_as(X)
+
+
+class IAOGDecoder(nn.Module):
+    def __init__(self, vocab_size):
+        super().__init__()
+        self.num_hiddens = M.HIDDEN_SIZE
+        self.num_blks = M.NUM_HIDDEN_LAYERS
+        self.embedding = nn.Embedding(vocab_size, self.num_hiddens)
+        self.pos_encoding = PositionalEncoding()
+        self.blks = nn.Sequential()
+        for i in range(self.num_blks):
+            self.blks.add_module("block" + str(i), TransformerDecoderBlock(i))
+        self.dense = nn.Linear(self.num_hiddens, vocab_size)
+        self.dense.weight = self.embedding.weight
+        self.compute_dtype = None
+
+    def init_state(self, enc_outputs, enc_valid_lens):
+        return [enc_outputs, enc_valid_lens, [None] * self.num_blks]
+
+    def forward(self, X, state, enc_attention_mask=None, is_train=True):
+        X = self.pos_encoding(self.embedding(X) * math.sqrt(self.num_hiddens))
+        if self.compute_dtype is not None:
+            X = X.to(self.compute_dtype)
+        self._attention_weights = [[None] * len(self.blks) for _ in range(2)]
+        for i, blk in enumerate(self.blks):
+            X, state = blk(X, state, enc_attention_mask=enc_attention_mask, is_train=is_train)
+            self._attention_weights[0][i] = blk.attention1.attention_weights
+            self._attention_weights[1][i] = blk.attention2.attention_weights
+        B, T, H = X.shape
+        return Fn.linear(X.reshape(B * T, H), self.dense.weight, self.dense.bias).view(B, T, -1)
+
+    @property
+    def attention_weights(self):
+        return self._attention_weights

@@ -1,0 +1,158 @@
+"""Model-level parity of the CUDA path (through the C ABI) with (a) the committed golden outputs of the reference
+itself and (b) the oracle run on the same seeded inputs.
+
+Bars (north_star): fp32 mode 1e-4 relative on logits and gradients; bf16 mode 2e-2 relative on logits with
+>= 99.9 % argmax agreement per aspect. "relative" = max|a-b| / max|b| (see _util.rel_err)."""
+import pytest
+import torch
+
+from _util import golden_inputs, golden_sample, load_golden, pkg, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+L = pkg("_lib")
+
+
+def build_model(dims, params, dtype=None, rows="full", engine=0):
+    M = pkg("fcmf_framework.mm_modeling")
+    M.HIDDEN_SIZE, M.NUM_ATTENTION_HEADS, M.INTERMEDIATE_SIZE = dims.hidden, dims.heads, dims.inter
+    FCMF = pkg("fcmf_framework.fcmf_multimodal").FCMF
+    model = FCMF(None, num_labels=dims.num_labels, num_imgs=dims.num_imgs, num_roi=dims.num_roi)
+    missing, unexpected = model.load_state_dict(params, strict=True)
+    model = model.cuda().eval()
+    model.encoder.compute_dtype, model.encoder.rows, model.encoder.engine = dtype, rows, engine
+    M.HIDDEN_SIZE, M.NUM_ATTENTION_HEADS, M.INTERMEDIATE_SIZE = 768, 12, 3072
+    return model
+
+
+def run_folded(model, batch, dims, rows):
+    seq = batch["sequence_output"].cuda().clone().requires_grad_(True)
+    B, A = dims.batch, dims.aspects
+    logits, loss = model.fuse_all_aspects(seq, batch["visual_embeds_att"].cuda(), batch["roi_embeds_att"].cuda(),
+                                          batch["roi_coors"].cuda(), batch["added_attention_mask"].cuda().reshape(B * A, -1),
+                                          batch["labels"].cuda(), rows=rows)
+    loss.backward()
+    return logits, loss, seq.grad
+
+
+@pytest.mark.parametrize("rows", ["full", "live"])
+@pytest.mark.parametrize("name", ["base_small", "base_roi7", "large_small", "base_cfg1_b1"])
+def test_fp32_matches_reference_golden(name, rows):
+    z, dims = load_golden(name)
+    params, batch = golden_inputs(z, dims)
+    model = build_model(dims, params, torch.float32, rows, L.ENGINE_SIMT)
+    logits, loss, dseq = run_folded(model, batch, dims, rows)
+    TOL = 1e-4
+    assert rel_err(logits, torch.from_numpy(z["logits"])) < TOL
+    assert abs(loss.item() - float(z["loss"])) < TOL * max(1.0, abs(float(z["loss"])))
+    stride = int(z["sample_stride"])
+    gold = torch.from_numpy(z["d_sequence_output"]).reshape(-1)
+    got = dseq.reshape(-1).cpu() if gold.numel() == dseq.numel() else golden_sample(dseq, stride)
+    assert rel_err(got, gold) < TOL
+    for k, v in model.named_parameters():
+        g = torch.from_numpy(z["gsample/" + k])
+        assert v.grad is not None, k
+        assert rel_err(golden_sample(v.grad, stride), g) < TOL, k
+
+
+def test_per_aspect_forward_equals_folded_launch():
+    """6 model(...) calls (run_multimodal_fcmf.py:464-475) == one folded call, logits and gradients."""
+    z, dims = load_golden("base_small")
+    params, batch = golden_inputs(z, dims)
+    model = build_model(dims, params, torch.float32, "full", L.ENGINE_SIMT)
+
+    class Stub(torch.nn.Module):
+        def forward(self, input_ids, token_type_ids, attention_mask):
+            return input_ids, None, None
+    model.encoder.bert = Stub()
+    seq = batch["sequence_output"].cuda().clone().requires_grad_(True)
+    total, outs = 0, []
+    for a in range(dims.aspects):
+        lg = model(input_ids=seq[:, a], token_type_ids=None, attention_mask=None,
+                   added_attention_mask=batch["added_attention_mask"][:, a].cuda(),
+                   visual_embeds_att=batch["visual_embeds_att"].cuda(), roi_embeds_att=batch["roi_embeds_att"].cuda(),
+                   roi_coors=batch["roi_coors"].cuda())
+        total = total + torch.nn.functional.cross_entropy(lg, batch["labels"][:, a].cuda())
+        outs.append(lg)
+    total.backward()
+    g_loop = {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}
+    dseq_loop = seq.grad.clone()
+    model.zero_grad()
+    logits, loss, dseq = run_folded(model, batch, dims, "full")
+    assert rel_err(torch.stack(outs, 1), logits) < 1e-5 and abs(total.item() - loss.item()) < 1e-5
+    assert rel_err(dseq_loop, dseq) < 1e-4
+    for k, v in model.named_parameters():
+        if v.grad is not None:
+            assert rel_err(g_loop[k], v.grad) < 1e-4, k
+    assert rel_err(torch.stack(outs, 1), torch.from_numpy(z["logits"])) < 1e-4
+
+
+@pytest.mark.parametrize("engine", [L.ENGINE_SIMT, L.ENGINE_AUTO])
+@pytest.mark.parametrize("rows", ["full", "live"])
+def test_bf16_mode_logits_and_argmax(rows, engine):
+    from oracle import fcmf_oracle as O
+    dims = synth.FusionDims(batch=24, aspects=6, seq_len=40, num_imgs=3, num_roi=4)
+    params = synth.make_params(dims, seed=7)
+    batch = synth.make_batch(dims, seed=11, mask="bernoulli")
+    with torch.no_grad():
+        ref, _ = O.aspect_loop(batch["sequence_output"], batch["visual_embeds_att"], batch["roi_embeds_att"],
+                               batch["roi_coors"], batch["added_attention_mask"], batch["labels"], params,
+                               dims.heads, dims.num_imgs, dims.num_roi)
+    model = build_model(dims, params, torch.bfloat16, rows, engine)
+    logits, loss, dseq = run_folded(model, batch, dims, rows)
+    assert rel_err(logits, ref) < 2e-2
+    top2 = ref.topk(2, -1).values
+    decided = (top2[..., 0] - top2[..., 1]) > 2e-2 * ref.abs().max()        # ties inside the tolerance cannot count
+    agree = (logits.argmax(-1).cpu() == ref.argmax(-1))
+    for a in range(dims.aspects):
+        m = decided[:, a]
+        assert agree[:, a][m].float().mean().item() >= 0.999
+    assert torch.isfinite(dseq.float()).all()
+
+
+def test_bf16_gradients_track_fp32_reference():
+    z, dims = load_golden("base_small")
+    params, batch = golden_inputs(z, dims)
+    model = build_model(dims, params, torch.bfloat16, "full", L.ENGINE_AUTO)
+    logits, loss, dseq = run_folded(model, batch, dims, "full")
+    assert rel_err(logits, torch.from_numpy(z["logits"])) < 2e-2
+    assert rel_err(dseq.float().cpu().reshape(-1), torch.from_numpy(z["d_sequence_output"]).reshape(-1)) < 6e-2
+    stride = int(z["sample_stride"])
+    for k, v in model.named_parameters():
+        assert rel_err(golden_sample(v.grad, stride), torch.from_numpy(z["gsample/" + k])) < 8e-2, k
+
+
+def test_submodule_level_drop_in_matches_oracle():
+    """BertCrossEncoder / MultimodalEncoder / BoxMultiHeadedAttention / BertPooler called 1:1."""
+    from oracle import fcmf_oracle as O
+    dims = synth.FusionDims(batch=3, aspects=1, seq_len=20, num_imgs=1, num_roi=5)
+    params = synth.make_params(dims, seed=3)
+    model = build_model(dims, params, torch.float32, "full", L.ENGINE_SIMT)
+    enc = model.encoder
+    g = torch.Generator().manual_seed(0)
+    s1, s2 = torch.randn(3, 20, 768, generator=g), torch.randn(3, 49, 768, generator=g)
+    m = (torch.rand(3, 49, generator=g) < 0.8).long()
+    m[:, 0] = 1
+    ext = O.extended_mask(m, 49)
+    want = O.encoder_layer(s1, s2, ext, params, "encoder.text2img_attention.layer.0", dims.heads)
+    got = enc.text2img_attention(s1.cuda(), s2.cuda(), ext.cuda())[-1]
+    assert rel_err(got, want) < 1e-4
+    ext2 = O.extended_mask(m, 20)
+    want = O.encoder_layer(s1, s1, ext2, params, "encoder.mm_attention.layer.0", dims.heads)
+    assert rel_err(enc.mm_attention(s1.cuda(), ext2.cuda())[-1], want) < 1e-4
+    boxes = synth.make_batch(dims, seed=5)["roi_coors"][:, 0]
+    x = torch.randn(3, 5, 768, generator=g)
+    want = O.box_multihead_attention(x, boxes, params, "encoder.box_head")
+    assert rel_err(enc.box_head(x.cuda(), x.cuda(), x.cuda(), boxes.cuda()), want) < 1e-4
+    assert rel_err(enc.text2img_pooler(s1.cuda()), O.first_token_pooler(s1, params, "encoder.text2img_pooler")) < 1e-4
+
+
+def test_missing_inputs_raise_like_the_reference_would():
+    dims = synth.FusionDims(batch=1, aspects=1, seq_len=8, num_imgs=1, num_roi=2)
+    model = build_model(dims, synth.make_params(dims), torch.float32)
+    b = synth.make_batch(dims)
+    seq = b["sequence_output"][:, 0].cuda()
+    with pytest.raises(ValueError):
+        model.encoder.fuse(seq, b["visual_embeds_att"].cuda(), b["roi_embeds_att"].cuda(), None, b["added_attention_mask"][:, 0].cuda())
+    with pytest.raises(RuntimeError, match="shorter"):
+        model.encoder.fuse(seq, b["visual_embeds_att"].cuda(), b["roi_embeds_att"].cuda(), b["roi_coors"].cuda(),
+                           b["added_attention_mask"][:, 0, :20].cuda())

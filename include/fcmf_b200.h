@@ -37,6 +37,8 @@ enum {
 
 int fcmf_abi_version(void);
 const char* fcmf_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+long long fcmf_kernel_launches(void);
 /* sm count, compute capability; fails (FCMF_ERR_CUDA) when no device is present. */
 int fcmf_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -103,6 +105,9 @@ typedef struct {
   float scale;
 } fcmf_attn_desc;
 
+/* Attention engine for subsequent calls: FCMF_ENGINE_AUTO (tcgen05 for bf16, head_dim 64, no bias, 16 <= L <= 320;
+ * CUDA-core otherwise), FCMF_ENGINE_SIMT or FCMF_ENGINE_TCGEN05 (fail if unsupported). Process-wide. */
+int fcmf_set_attn_engine(int engine);
 int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, float* lse, int dtype, void* stream);
 /* Per-problem gradients (the caller reduces rows shared between problems with fcmf_gather_sum_rows):
  * dq [NP, Lq, heads*dh], dk/dv [NP, Lk, heads*dh] in `dtype`, dbias [NP, heads, Lq, Lk] fp32 or NULL.

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "fcmf_dtanh": [_vp, _vp, _vp, _i64, C.c_int, _vp],
     "fcmf_cast_matrix": [_vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp],
     "fcmf_cast_to_f32": [_vp, _vp, _i64, C.c_int, _vp],
+    "fcmf_set_attn_engine": [C.c_int],
     "fcmf_attn_fwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, C.c_int, _vp],
     "fcmf_attn_bwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp],
     "fcmf_box_geometry_fwd": [_vp, _vp, _vp, C.POINTER(_f32), _vp, _vp, _i64, _i32, _i32, _vp],
@@ -73,6 +74,8 @@ def load() -> C.CDLL:
             fn.restype = C.c_int
         lib.fcmf_last_error.argtypes = []
         lib.fcmf_last_error.restype = C.c_char_p
+        lib.fcmf_kernel_launches.argtypes = []
+        lib.fcmf_kernel_launches.restype = C.c_longlong
         if lib.fcmf_abi_version() != 1:
             raise RuntimeError(f"libfcmf_b200.so ABI version {lib.fcmf_abi_version()} != 1; rebuild")
         _lib = lib
@@ -88,5 +91,10 @@ def call(name: str, *args) -> None:
     launches += 1
 
 
+def kernel_launches() -> int:
+    """Kernels launched by libfcmf_b200.so in this process so far."""
+    return int(load().fcmf_kernel_launches())
+
+
 def exported_symbols():
-    return list(PROTOTYPES) + ["fcmf_last_error"]
+    return list(PROTOTYPES) + ["fcmf_last_error", "fcmf_kernel_launches"]

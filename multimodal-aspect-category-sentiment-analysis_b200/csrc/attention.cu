@@ -5,29 +5,14 @@
 // lane<->column accumulations); each warp then owns whole output rows, so no atomics are needed.
 // Backward follows the flash formulation: probabilities are recomputed from the saved log-sum-exp.
 #include "common.cuh"
+#include "attn.h"
+#include <atomic>
 
 namespace fcmf {
 
 constexpr int AT_WARPS = 8;
 constexpr int AT_THREADS = AT_WARPS * 32;
 constexpr int AT_MAX_DPL = 4;                 // head dim <= 128
-
-struct SegDev { const void* ptr; int64_t ld; int rows; const int32_t* idx; };
-struct AttnDev {
-  SegDev q[2], k[2], v[2];
-  const float* mask_add; int64_t ld_mask; int mask_div;
-  const float* bias;
-  int NP, heads, dh, Lq, Lk;
-  float scale;
-};
-
-template <typename T>
-__device__ __forceinline__ const T* seg_row(const SegDev (&s)[2], int p, int r, int h, int dh) {
-  const SegDev& g = (r < s[0].rows) ? s[0] : s[1];
-  const int rl = (r < s[0].rows) ? r : r - s[0].rows;
-  const int64_t grp = g.idx ? g.idx[p] : p;
-  return reinterpret_cast<const T*>(g.ptr) + (grp * g.rows + rl) * g.ld + (int64_t)h * dh;
-}
 
 // Stage `rows` x dh of a two-segment matrix into smem (fp32, stride dh+1).
 template <typename T>
@@ -210,6 +195,9 @@ attn_bwd_dkv_kernel(AttnDev a, const T* __restrict__ dctx, int64_t lddctx, const
   }
 }
 
+static std::atomic<int> g_attn_engine{0};
+int attn_engine() { return g_attn_engine.load(std::memory_order_relaxed); }
+
 static int to_dev(const fcmf_attn_desc* d, AttnDev* o) {
   FCMF_CHECK_ARG(d != nullptr, "attn: null descriptor");
   for (int s = 0; s < 2; ++s) {
@@ -241,11 +229,23 @@ static int set_smem(K kernel, size_t bytes) {
 
 using namespace fcmf;
 
+extern "C" int fcmf_set_attn_engine(int engine) {
+  FCMF_CHECK_ARG(engine >= FCMF_ENGINE_AUTO && engine <= FCMF_ENGINE_TCGEN05, "set_attn_engine: bad engine %d", engine);
+  g_attn_engine.store(engine, std::memory_order_relaxed);
+  return 0;
+}
+
 extern "C" int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, float* lse, int dtype, void* stream) {
   AttnDev a;
   if (int r = to_dev(d, &a)) return r;
   FCMF_CHECK_ARG(dtype == FCMF_F32 || dtype == FCMF_BF16, "attn_fwd: bad dtype %d", dtype);
   if (a.NP == 0) return 0;
+  {
+    const int eng = attn_engine();
+    const bool ok = dtype == FCMF_BF16 && attn_tc_supported(a, ldctx, ctx);
+    if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_fwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
+    if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_fwd(a, ctx, ldctx, lse, as_stream(stream));
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * a.Lk * (a.dh + 1) + (size_t)AT_WARPS * (a.dh + a.Lk));
   const unsigned grid = (unsigned)(a.NP * a.heads);
   cudaStream_t st = as_stream(stream);
@@ -269,6 +269,12 @@ extern "C" int fcmf_attn_bwd(const fcmf_attn_desc* d, const void* ctx, int64_t l
   FCMF_CHECK_ARG(lse && delta && dq && dk && dv, "attn_bwd: null buffer");
   if (a.NP == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  {
+    const int eng = attn_engine();
+    const bool ok = dtype == FCMF_BF16 && dbias == nullptr && attn_tc_supported(a, ldctx, ctx) && (lddctx % 8) == 0;
+    if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_bwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
+    if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_bwd(a, ctx, ldctx, dctx, lddctx, lse, delta, dq, dk, dv, st);
+  }
   const size_t smem_q = sizeof(float) * ((size_t)2 * a.Lk * (a.dh + 1) + (size_t)AT_WARPS * (2 * a.dh + a.Lk));
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a.Lq * (a.dh + 1) + 2 * (size_t)a.Lq + (size_t)AT_WARPS * (2 * a.dh + 2 * a.Lq));
   const unsigned grid = (unsigned)(a.NP * a.heads);

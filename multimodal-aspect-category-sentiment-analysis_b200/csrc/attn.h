@@ -1,0 +1,32 @@
+// Internal attention interface shared by the CUDA-core engine (attention.cu) and the tcgen05 engine (attn_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fcmf {
+
+struct SegDev { const void* ptr; int64_t ld; int rows; const int32_t* idx; };
+struct AttnDev {
+  SegDev q[2], k[2], v[2];
+  const float* mask_add; int64_t ld_mask; int mask_div;
+  const float* bias;
+  int NP, heads, dh, Lq, Lk;
+  float scale;
+};
+
+template <typename T>
+__device__ __forceinline__ const T* seg_row(const SegDev (&s)[2], int p, int r, int h, int dh) {
+  const SegDev& g = (r < s[0].rows) ? s[0] : s[1];
+  const int rl = (r < s[0].rows) ? r : r - s[0].rows;
+  const int64_t grp = g.idx ? g.idx[p] : p;
+  return reinterpret_cast<const T*>(g.ptr) + (grp * g.rows + rl) * g.ld + (int64_t)h * dh;
+}
+
+
+// tcgen05 engine (attn_tc.cu): bf16, head_dim 64, no per-pair bias
+bool attn_tc_supported(const AttnDev& a, int64_t ldctx, const void* ctx);
+int attn_tc_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStream_t st);
+int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
+                float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
+int attn_engine();      // 0 auto, 1 CUDA-core, 2 tcgen05 (fcmf_set_attn_engine)
+
+}  // namespace fcmf

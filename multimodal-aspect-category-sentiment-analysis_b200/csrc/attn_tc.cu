@@ -1,0 +1,546 @@
+// tcgen05 / TMEM folded attention for head_dim 64, bf16 (forward, dQ, dK/dV).
+//
+// One CTA = one (problem, head, 128-row tile). Everything is organised in 64-wide blocks, so every contraction is
+// the same "block MMA": D[128 x 64] (+)= A[128 x 64] . B[64 x 64], issued as four tcgen05.mma (M128 N64 K16) by one
+// thread, operands in shared memory in the 128-byte-swizzled row format (row r at r*128 B, 16-byte chunk c stored at
+// chunk c ^ (r & 7)) that both TMA and the UMMA descriptors of gemm_tc.cu use:
+//   * "row operand"  (K-major):  rows = M or N index, the 64 columns are the reduction  (Q.K^T, dO.V^T, K.Q^T, V.dO^T)
+//   * "col operand"  (MN-major): rows = reduction index, the 64 columns are N            (P.V, dS.K, P^T.dO, dS^T.Q)
+// the SAME shared-memory image serves as either, only the descriptor differs.
+// Scores live in TMEM; each of the 128 threads owns one TMEM lane (= one query row, or one key row in the dK/dV
+// kernel), reads it with tcgen05.ld, does the softmax arithmetic in registers and writes the bf16 probabilities
+// back to shared memory as the A operand of the second contraction. Several CTAs share an SM (48-112 KB of shared
+// memory, 128-256 TMEM columns each), which is what overlaps one CTA's global loads with another's MMAs.
+//
+// Reference semantics: BertCoAttention/BertSelfAttention.forward (mm_modeling.py:193-266): scale before the mask
+// add, additive -10000 mask on the keys, softmax over keys, context = P.V; backward = autograd of the same.
+#include "common.cuh"
+#include "attn.h"
+
+namespace fcmf {
+
+constexpr int ATC_THREADS = 128;
+constexpr int ATC_TILE = 128;                   // rows per CTA tile (UMMA M)
+constexpr int ATC_BLK = 64;                     // block width
+constexpr uint32_t ATC_TILE_BYTES = ATC_TILE * 128;   // 16 KB
+constexpr uint32_t ATC_BLK_BYTES = ATC_BLK * 128;     // 8 KB
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void a_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool a_mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(a_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (a_mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!a_mbar_try(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 6000000000LL) {
+      printf("fcmf attn_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void a_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void a_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a_smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void a_tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void a_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void a_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void a_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t a_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;                       // 8-row groups are 1024 B apart
+  d |= (uint64_t)1 << 46;                                 // descriptor version
+  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t a_idesc(int b_mn_major) {             // bf16 x bf16 -> f32, M = 128, N = 64
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(64 >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+// D[128x64] (+)= A_rowop[128 x 64] . B_rowop[64 x 64]^T   (reduction over the 64 columns of both)
+__device__ __forceinline__ void block_mma_rr(uint32_t tmem_d, uint32_t a_tile, uint32_t b_blk, bool accumulate) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    a_umma(tmem_d, a_desc(a_tile + k * 32, 16), a_desc(b_blk + k * 32, 16), a_idesc(0), (accumulate || k > 0) ? 1u : 0u);
+}
+// D[128x64] (+)= A_rowop[128 x 64] . B_colop[64 rows(reduction) x 64 (N)]; only the first `ksteps` 16-row steps
+__device__ __forceinline__ void block_mma_rc(uint32_t tmem_d, uint32_t a_tile, uint32_t b_blk, bool accumulate, int ksteps) {
+  for (int k = 0; k < ksteps; ++k)
+    a_umma(tmem_d, a_desc(a_tile + k * 32, 16), a_desc(b_blk + k * 2048, 8192), a_idesc(1), (accumulate || k > 0) ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------- tile staging
+__device__ __forceinline__ uint32_t swz(int r, int chunk) { return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)); }
+
+// rows [row0, row0+tile_rows) of a segmented [L x 64] bf16 matrix of (problem p, head h) -> swizzled tile; rows >= L are 0
+__device__ __forceinline__ void stage_seg(uint8_t* tile, const SegDev (&s)[2], int p, int h, int row0, int tile_rows, int L) {
+  for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
+    const int r = e >> 3, c = e & 7, gr = row0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gr < L) v = *reinterpret_cast<const uint4*>(seg_row<bf16>(s, p, gr, h, 64) + c * 8);
+    *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
+  }
+}
+// same for a plain [NP*L, ld] activation (ctx / dctx)
+__device__ __forceinline__ void stage_plain(uint8_t* tile, const bf16* base, int64_t ld, int64_t prow0, int h, int row0,
+                                            int tile_rows, int L) {
+  for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
+    const int r = e >> 3, c = e & 7, gr = row0 + r;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gr < L) v = *reinterpret_cast<const uint4*>(base + (prow0 + gr) * ld + (int64_t)h * 64 + c * 8);
+    *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
+  }
+}
+// thread-owned row: write 32 consecutive bf16 (cols c0..c0+31 of a 64-col block) of row r into a swizzled tile
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int c0, const float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 w;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hh[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+    *reinterpret_cast<uint4*>(tile + swz(r, (c0 >> 3) + g)) = w;
+  }
+}
+
+struct AtcShared {                               // lives at the start of dynamic smem (after 1024-alignment)
+  uint64_t bar;
+  uint32_t tmem;
+};
+
+__device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// ------------------------------------------------------------------------------------------- forward
+// smem: [Q tile 16K = P block 0 (Q is dead once S is in TMEM)][K blocks NKB*8K][V blocks NKB*8K][P blocks 1.. (NKB-1)*16K]
+//       [mask NKB*64 f32][AtcShared]
+template <int NKB>
+__global__ void __launch_bounds__(ATC_THREADS)
+attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __restrict__ lse, int mtiles) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = align1k(raw);
+  uint8_t* Qs = sm;
+  uint8_t* Ks = Qs + ATC_TILE_BYTES;
+  uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
+  uint8_t* Px = Vs + NKB * ATC_BLK_BYTES;
+  float* msk = reinterpret_cast<float*>(Px + (NKB - 1) * ATC_TILE_BYTES);
+  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
+  constexpr uint32_t kCols = (NKB + 1) * 64 <= 128 ? 128 : ((NKB + 1) * 64 <= 256 ? 256 : 512);
+  auto Pblk = [&](int b) -> uint8_t* { return b == 0 ? Qs : Px + (b - 1) * ATC_TILE_BYTES; };
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.x % mtiles;
+  const int ph = blockIdx.x / mtiles;
+  const int p = ph / a.heads, h = ph % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE;
+
+  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
+  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
+  stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
+  stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
+  stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
+  a_fence_async();
+  a_tc_before();
+  __syncthreads();
+  a_tc_after();
+  const uint32_t tm = sh->tmem;
+  const uint32_t tS = tm, tO = tm + NKB * 64;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int b = 0; b < NKB; ++b) block_mma_rr(tS + b * 64, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);
+    a_commit(&sh->bar);
+  }
+  a_mbar_wait(&sh->bar, 0);
+  a_tc_after();
+
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < NKB * 2; ++c) {
+    uint32_t r[32];
+    a_tmem_ld32(tS + lane_addr + c * 32, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * a.scale + msk[c * 32 + j]);
+  }
+  float sum = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < NKB * 2; ++c) {
+    uint32_t r[32];
+    float v[32];
+    a_tmem_ld32(tS + lane_addr + c * 32, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = __expf(__uint_as_float(r[j]) * a.scale + msk[c * 32 + j] - mx);
+      sum += v[j];
+    }
+    store_row32(Pblk(c >> 1), tid, (c & 1) * 32, v);
+  }
+  a_fence_async();
+  a_tc_before();
+  __syncthreads();
+  a_tc_after();
+  if (tid == 0) {
+    const int ksteps_total = (Lk + 15) >> 4;
+#pragma unroll
+    for (int b = 0; b < NKB; ++b) {
+      const int ks = min(4, ksteps_total - b * 4);
+      if (ks > 0) block_mma_rc(tO, a_smem_u32(Pblk(b)), a_smem_u32(Vs + b * ATC_BLK_BYTES), b > 0, ks);
+    }
+    a_commit(&sh->bar);
+  }
+  a_mbar_wait(&sh->bar, 1);
+  a_tc_after();
+  const int row = row0 + tid;
+  const float inv = 1.0f / sum;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    a_tmem_ld32(tO + lane_addr + c * 32, r);
+    if (row < Lq) {
+      bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + c * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * inv, __uint_as_float(r[g * 8 + 2 * j + 1]) * inv);
+        *reinterpret_cast<uint4*>(o + g * 8) = w;
+      }
+    }
+  }
+  if (row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = mx + __logf(sum);
+  a_tc_before();
+  __syncthreads();
+  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+}
+
+// ------------------------------------------------------------------------------------------- dQ (+ delta)
+// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
+template <int NKB>
+__global__ void __launch_bounds__(ATC_THREADS)
+attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const bf16* __restrict__ dctx, int64_t lddctx,
+                  const float* __restrict__ lse, bf16* __restrict__ dq, float* __restrict__ delta, int mtiles) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = align1k(raw);
+  uint8_t* Qs = sm;
+  uint8_t* Gs = Qs + ATC_TILE_BYTES;
+  uint8_t* Ks = Gs + ATC_TILE_BYTES;
+  uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
+  uint8_t* Ds = Vs + NKB * ATC_BLK_BYTES;
+  float* msk = reinterpret_cast<float*>(Ds + ATC_TILE_BYTES);
+  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
+  constexpr uint32_t kCols = 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.x % mtiles;
+  const int ph = blockIdx.x / mtiles;
+  const int p = ph / a.heads, h = ph % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE, HD = a.heads * 64;
+
+  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
+  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
+  stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
+  stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
+  stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
+  stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
+
+  // delta_i = dO_i . O_i  (thread-owned row, straight from global)
+  const int row = row0 + tid;
+  const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
+  float dl = 0.f, l = 0.f;
+  if (row < Lq) {
+    const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64;
+    const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      Vec16<bf16> x, y;
+      x.load(o + c * 8); y.load(g + c * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dl = fmaf(x.v[j], y.v[j], dl);
+    }
+    l = lse[stat];
+    delta[stat] = dl;
+  }
+  a_fence_async();
+  a_tc_before();
+  __syncthreads();
+  a_tc_after();
+  const uint32_t tm = sh->tmem;
+  const uint32_t tS = tm, tP = tm + 64, tQ = tm + 128;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  uint32_t parity = 0;
+  const int nblk = (Lk + 63) >> 6;
+
+#pragma unroll 1
+  for (int b = 0; b < nblk; ++b) {
+    if (tid == 0) {
+      block_mma_rr(tS, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);      // S_b  = Q . K_b^T
+      block_mma_rr(tP, a_smem_u32(Gs), a_smem_u32(Vs + b * ATC_BLK_BYTES), false);      // dP_b = dO . V_b^T
+      a_commit(&sh->bar);
+    }
+    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // also orders the previous block's dQ MMA (reads Ds) before the rewrite below
+    a_tc_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rs[32], rp[32];
+      float v[32];
+      a_tmem_ld32(tS + lane_addr + c * 32, rs);
+      a_tmem_ld32(tP + lane_addr + c * 32, rp);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __expf(__uint_as_float(rs[j]) * a.scale + msk[b * 64 + c * 32 + j] - l);
+        v[j] = (row < Lq) ? pj * (__uint_as_float(rp[j]) - dl) : 0.f;
+      }
+      store_row32(Ds, tid, c * 32, v);
+    }
+    a_fence_async();
+    a_tc_before();
+    __syncthreads();
+    a_tc_after();
+    if (tid == 0) {
+      const int ks = min(4, ((Lk + 15) >> 4) - b * 4);
+      block_mma_rc(tQ, a_smem_u32(Ds), a_smem_u32(Ks + b * ATC_BLK_BYTES), b > 0, ks);  // dQ += dS_b . K_b
+      if (b == nblk - 1) a_commit(&sh->bar);
+    }
+  }
+  a_mbar_wait(&sh->bar, parity);
+  a_tc_after();
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    a_tmem_ld32(tQ + lane_addr + c * 32, r);
+    if (row < Lq) {
+      bf16* o = dq + ((int64_t)p * Lq + row) * HD + (int64_t)h * 64 + c * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * a.scale, __uint_as_float(r[g * 8 + 2 * j + 1]) * a.scale);
+        *reinterpret_cast<uint4*>(o + g * 8) = w;
+      }
+    }
+  }
+  a_tc_before();
+  __syncthreads();
+  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+}
+
+// ------------------------------------------------------------------------------------------- dK, dV
+// CTA tile = 128 KEY rows. smem: [K 16K][V 16K][Q NQB*8K][dO NQB*8K][P^T 16K][dS^T 16K][lse NQB*64][delta NQB*64][AtcShared]
+// TMEM: S^T 64 | dP^T 64 | dV 64 | dK 64
+template <int NQB>
+__global__ void __launch_bounds__(ATC_THREADS)
+attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, const float* __restrict__ lse,
+                   const float* __restrict__ delta, bf16* __restrict__ dk, bf16* __restrict__ dv, int ktiles) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = align1k(raw);
+  uint8_t* Ks = sm;
+  uint8_t* Vs = Ks + ATC_TILE_BYTES;
+  uint8_t* Qs = Vs + ATC_TILE_BYTES;
+  uint8_t* Gs = Qs + NQB * ATC_BLK_BYTES;
+  uint8_t* Pt = Gs + NQB * ATC_BLK_BYTES;
+  uint8_t* St = Pt + ATC_TILE_BYTES;
+  float* ls = reinterpret_cast<float*>(St + ATC_TILE_BYTES);
+  float* dls = ls + NQB * 64;
+  AtcShared* sh = reinterpret_cast<AtcShared*>(dls + NQB * 64);
+  constexpr uint32_t kCols = 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kt = blockIdx.x % ktiles;
+  const int ph = blockIdx.x / ktiles;
+  const int p = ph / a.heads, h = ph % a.heads;
+  const int Lq = a.Lq, Lk = a.Lk, key0 = kt * ATC_TILE, HD = a.heads * 64;
+
+  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
+  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
+  stage_seg(Ks, a.k, p, h, key0, ATC_TILE, Lk);
+  stage_seg(Vs, a.v, p, h, key0, ATC_TILE, Lk);
+  stage_seg(Qs, a.q, p, h, 0, NQB * 64, Lq);
+  stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, 0, NQB * 64, Lq);
+  const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
+  for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
+    ls[i] = i < Lq ? lse[stat0 + i] : INFINITY;          // exp(s - inf) = 0 for the padded queries
+    dls[i] = i < Lq ? delta[stat0 + i] : 0.f;
+  }
+  const int key = key0 + tid;
+  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  const float mk = (key < Lk && madd) ? madd[key] : 0.f;
+  a_fence_async();
+  a_tc_before();
+  __syncthreads();
+  a_tc_after();
+  const uint32_t tm = sh->tmem;
+  const uint32_t tS = tm, tP = tm + 64, tV = tm + 128, tK = tm + 192;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  uint32_t parity = 0;
+  const int nblk = (Lq + 63) >> 6;
+
+#pragma unroll 1
+  for (int b = 0; b < nblk; ++b) {
+    if (tid == 0) {
+      block_mma_rr(tS, a_smem_u32(Ks), a_smem_u32(Qs + b * ATC_BLK_BYTES), false);      // S^T_b  = K . Q_b^T
+      block_mma_rr(tP, a_smem_u32(Vs), a_smem_u32(Gs + b * ATC_BLK_BYTES), false);      // dP^T_b = V . dO_b^T
+      a_commit(&sh->bar);
+    }
+    a_mbar_wait(&sh->bar, parity); parity ^= 1;
+    a_tc_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rs[32], rp[32];
+      float pv[32], dsv[32];
+      a_tmem_ld32(tS + lane_addr + c * 32, rs);
+      a_tmem_ld32(tP + lane_addr + c * 32, rp);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int qi = b * 64 + c * 32 + j;
+        const float pj = (key < Lk) ? __expf(__uint_as_float(rs[j]) * a.scale + mk - ls[qi]) : 0.f;
+        pv[j] = pj;
+        dsv[j] = pj * (__uint_as_float(rp[j]) - dls[qi]);
+      }
+      store_row32(Pt, tid, c * 32, pv);
+      store_row32(St, tid, c * 32, dsv);
+    }
+    a_fence_async();
+    a_tc_before();
+    __syncthreads();
+    a_tc_after();
+    if (tid == 0) {
+      const int ks = min(4, ((Lq + 15) >> 4) - b * 4);
+      block_mma_rc(tV, a_smem_u32(Pt), a_smem_u32(Gs + b * ATC_BLK_BYTES), b > 0, ks);  // dV += P^T_b . dO_b
+      block_mma_rc(tK, a_smem_u32(St), a_smem_u32(Qs + b * ATC_BLK_BYTES), b > 0, ks);  // dK += dS^T_b . Q_b
+      if (b == nblk - 1) a_commit(&sh->bar);
+    }
+  }
+  a_mbar_wait(&sh->bar, parity);
+  a_tc_after();
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    a_tmem_ld32((c < 2 ? tV : tK) + lane_addr + (c & 1) * 32, r);
+    if (key < Lk) {
+      const float sc = c < 2 ? 1.0f : a.scale;
+      bf16* o = (c < 2 ? dv : dk) + ((int64_t)p * Lk + key) * HD + (int64_t)h * 64 + (c & 1) * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * sc, __uint_as_float(r[g * 8 + 2 * j + 1]) * sc);
+        *reinterpret_cast<uint4*>(o + g * 8) = w;
+      }
+    }
+  }
+  a_tc_before();
+  __syncthreads();
+  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+}
+
+// ------------------------------------------------------------------------------------------- host dispatch
+static bool seg_ok(const SegDev& s) {
+  if (!s.ptr || s.rows == 0) return true;
+  return (reinterpret_cast<uintptr_t>(s.ptr) & 15u) == 0 && (s.ld % 8) == 0;
+}
+
+bool attn_tc_supported(const AttnDev& a, int64_t ldctx, const void* ctx) {
+  if (a.dh != 64 || a.bias != nullptr) return false;
+  if (a.Lq < 16 || a.Lk < 1 || a.Lk > 320 || a.Lq > 320) return false;      // NKB, NQB <= 5
+  if ((ldctx % 8) || (reinterpret_cast<uintptr_t>(ctx) & 15u)) return false;
+  for (int s = 0; s < 2; ++s)
+    if (!seg_ok(a.q[s]) || !seg_ok(a.k[s]) || !seg_ok(a.v[s])) return false;
+  return (int64_t)a.NP * a.heads * ((a.Lq + 127) / 128) < (1LL << 31);
+}
+
+template <typename K>
+static int set_smem_tc(K kernel, size_t bytes) {
+  FCMF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+#define ATC_DISPATCH(nb, CALL) \
+  switch (nb) { case 1: { CALL(1); } break; case 2: { CALL(2); } break; case 3: { CALL(3); } break; \
+                case 4: { CALL(4); } break; default: { CALL(5); } break; }
+
+int attn_tc_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStream_t st) {
+  const int nkb = (a.Lk + 63) / 64, mtiles = (a.Lq + 127) / 128;
+  const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
+#define CALL(NB)                                                                                              \
+  const size_t smem = 1024 + (size_t)NB * (2 * ATC_BLK_BYTES + ATC_TILE_BYTES + 256) + 64;                   \
+  if (int r = set_smem_tc(attn_tc_fwd_kernel<NB>, smem)) return r;                                            \
+  attn_tc_fwd_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (bf16*)ctx, ldctx, lse, mtiles);
+  ATC_DISPATCH(nkb, CALL)
+#undef CALL
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
+int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
+                float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
+  const int nkb = (a.Lk + 63) / 64, nqb = (a.Lq + 63) / 64;
+  const int mtiles = (a.Lq + 127) / 128, ktiles = (a.Lk + 127) / 128;
+  {
+    const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
+#define CALL(NB)                                                                                              \
+    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 64;             \
+    if (int r = set_smem_tc(attn_tc_dq_kernel<NB>, smem)) return r;                                           \
+    attn_tc_dq_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse, (bf16*)dq, delta, mtiles);
+    ATC_DISPATCH(nkb, CALL)
+#undef CALL
+    FCMF_LAUNCH_OK();
+  }
+  {
+    const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * ktiles);
+#define CALL(NB)                                                                                              \
+    const size_t smem = 1024 + 4 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 512) + 64;             \
+    if (int r = set_smem_tc(attn_tc_dkv_kernel<NB>, smem)) return r;                                          \
+    attn_tc_dkv_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)dctx, lddctx, lse, delta, (bf16*)dk, (bf16*)dv, ktiles);
+    ATC_DISPATCH(nqb, CALL)
+#undef CALL
+    FCMF_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace fcmf

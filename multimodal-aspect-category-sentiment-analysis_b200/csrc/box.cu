@@ -54,21 +54,24 @@ __global__ void box_geometry_dz_kernel(const float* __restrict__ emb, const floa
   dz[t] = (z >= 1e-6f) ? dbias[t] / z : 0.f;
 }
 
-// d_w[h][c] += sum_pairs dz * emb[c] ; d_b[h] += sum_pairs dz.   grid = heads, block = 64 (+1 warp-less bias lane)
+// d_w[h][c] += sum_pairs dz * emb[c] ; d_b[h] += sum_pairs dz.   grid = (heads, chunks of pairs), block = 64
 __global__ void box_geometry_dw_kernel(const float* __restrict__ emb, const float* __restrict__ dz,
-                                       float* __restrict__ d_w, float* __restrict__ d_b, int64_t G, int NR, int heads) {
+                                       float* __restrict__ d_w, float* __restrict__ d_b, int64_t G, int NR, int heads,
+                                       int64_t pairs_per_block) {
   const int h = blockIdx.x, c = threadIdx.x;
   const int64_t npair = G * NR * NR;
+  const int64_t lo = (int64_t)blockIdx.y * pairs_per_block;
+  const int64_t hi = lo + pairs_per_block < npair ? lo + pairs_per_block : npair;
   float acc = 0.f, accb = 0.f;
-  for (int64_t pr = 0; pr < npair; ++pr) {
+  for (int64_t pr = lo; pr < hi; ++pr) {
     const int64_t g = pr / (NR * NR);
     const int ij = (int)(pr - g * NR * NR);
     const float d = dz[(g * heads + h) * NR * NR + ij];
     acc = fmaf(d, emb[pr * 64 + c], acc);
     accb += d;
   }
-  d_w[h * 64 + c] += acc;
-  if (c == 0) d_b[h] += accb;
+  atomicAdd(d_w + h * 64 + c, acc);
+  if (c == 0) atomicAdd(d_b + h, accb);
 }
 
 }  // namespace fcmf
@@ -96,7 +99,11 @@ extern "C" int fcmf_box_geometry_bwd(const float* emb, const float* wg_w, const 
   cudaStream_t st = as_stream(stream);
   box_geometry_dz_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(emb, wg_w, wg_b, dbias, dz_ws, G, NR, heads);
   FCMF_LAUNCH_OK();
-  box_geometry_dw_kernel<<<heads, 64, 0, st>>>(emb, dz_ws, d_wg_w, d_wg_b, G, NR, heads);
+  const int64_t npair = G * NR * NR;
+  int64_t chunks = (npair + 63) / 64;
+  if (chunks > 256) chunks = 256;
+  const int64_t per = (npair + chunks - 1) / chunks;
+  box_geometry_dw_kernel<<<dim3((unsigned)heads, (unsigned)((npair + per - 1) / per)), 64, 0, st>>>(emb, dz_ws, d_wg_w, d_wg_b, G, NR, heads, per);
   FCMF_LAUNCH_OK();
   return 0;
 }

@@ -25,7 +25,13 @@ int fail(int code, const char* fmt, ...);
                           __FILE__, __LINE__);                                                      \
   } while (0)
 
-#define FCMF_LAUNCH_OK() FCMF_CUDA_OK(cudaGetLastError())
+// every kernel launch of this library goes through this macro, so the counter is the number of OUR kernels launched
+void count_launch();
+#define FCMF_LAUNCH_OK()                    \
+  do {                                      \
+    ::fcmf::count_launch();                 \
+    FCMF_CUDA_OK(cudaGetLastError());       \
+  } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int sm_count();
@@ -91,7 +97,7 @@ __device__ __forceinline__ float gelu_erf(float x) {            // mm_modeling.p
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {       // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
 

@@ -1,6 +1,7 @@
 // Error plumbing, device queries and the ABI version entry points.
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 #include <mutex>
 
 namespace fcmf {
@@ -20,6 +21,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -34,7 +39,9 @@ int sm_count() {
 
 }  // namespace fcmf
 
+namespace fcmf { long long launches(); }
 extern "C" int fcmf_abi_version(void) { return FCMF_ABI_VERSION; }
+extern "C" long long fcmf_kernel_launches(void) { return fcmf::launches(); }
 
 extern "C" const char* fcmf_last_error(void) { return fcmf::last_error_ref().c_str(); }
 

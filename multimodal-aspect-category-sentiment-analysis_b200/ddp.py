@@ -1,0 +1,112 @@
+"""Data-parallel gradient reduction for the fusion parameters: bucketed NCCL all-reduce on a side stream, launched
+from autograd hooks in gradient-ready order so it overlaps the rest of backward.
+
+Samples are independent in the fusion path (no cross-sample op), so the batch is sharded by sample across ranks with
+no data-path collective; the only exchange is this all-reduce (DDP semantics: mean over ranks). The reference gets
+the same thing implicitly from torch DDP (run_multimodal_fcmf.py:238-240); the text encoder's 1.1 GB of gradients
+stays on stock DDP and is not touched here.
+
+Gradients live directly inside the flat bucket buffers (param.grad is a view), so no pack/unpack copies are made.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+# Grad-ready order of the fusion path's backward.
+BUCKET_ORDER: Sequence[Tuple[str, ...]] = (
+    ("classifier.", "text_pooler."),
+    ("encoder.text2img_pooler.", "encoder.text2roi_pooler."),
+    ("encoder.text2img_attention.",),
+    ("encoder.mm_attention.",),
+    ("encoder.box_head.", "encoder.roimap2text.", "encoder.vismap2text."),
+)
+
+
+def fusion_named_parameters(model: torch.nn.Module):
+    return [(n, p) for n, p in model.named_parameters() if not n.startswith("encoder.bert.") and p.requires_grad]
+
+
+class BucketedGradReducer:
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], process_group=None,
+                 bucket_order: Sequence[Tuple[str, ...]] = BUCKET_ORDER, average: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.average = average
+        named = list(named_params)
+        buckets: List[List[Tuple[str, torch.nn.Parameter]]] = [[] for _ in bucket_order]
+        rest: List[Tuple[str, torch.nn.Parameter]] = []
+        for n, p in named:
+            for b, prefixes in enumerate(bucket_order):
+                if n.startswith(prefixes):
+                    buckets[b].append((n, p))
+                    break
+            else:
+                rest.append((n, p))
+        if rest:
+            buckets.append(rest)
+        self.buckets = [b for b in buckets if b]
+        self.flat: List[torch.Tensor] = []
+        self._bucket_of: Dict[int, int] = {}
+        self._pending: List[int] = []
+        self._handles = []
+        dev = named[0][1].device
+        self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        for bi, bucket in enumerate(self.buckets):
+            n = sum(p.numel() for _, p in bucket)
+            flat = torch.zeros(n, dtype=torch.float32, device=dev)
+            off = 0
+            for _, p in bucket:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._bucket_of[id(p)] = bi
+                p.register_post_accumulate_grad_hook(self._on_grad_ready)
+            self.flat.append(flat)
+        self._reset_counts()
+
+    # ---- per step ---------------------------------------------------------------------------------------------
+    def _reset_counts(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._handles = []
+
+    def zero_grad(self):
+        """Zero the flat buffers in place (param.grad views stay attached)."""
+        for f in self.flat:
+            f.zero_()
+        self._reset_counts()
+
+    def _on_grad_ready(self, p: torch.nn.Parameter):
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and self.world > 1:
+            self._launch(bi)
+
+    def _launch(self, bi: int):
+        flat = self.flat[bi]
+        op = dist.ReduceOp.AVG if (self.average and flat.is_cuda) else dist.ReduceOp.SUM
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())        # gradients of this bucket are final
+            with torch.cuda.stream(self.side):
+                self._handles.append(dist.all_reduce(flat, op=op, group=self.group, async_op=True))
+        else:                                                         # gloo / CPU (tests)
+            dist.all_reduce(flat, op=op, group=self.group)
+            if self.average:
+                flat.div_(self.world)
+
+    def finish(self):
+        """Call after backward(): the compute stream waits for the outstanding all-reduces."""
+        if self.world > 1:
+            for bi, left in enumerate(self._pending):
+                if left > 0:          # a parameter received no gradient this step (unused): reduce what we have
+                    self._launch(bi)
+                    self._pending[bi] = 0
+            for h in self._handles:
+                h.wait()
+            if self.side is not None:
+                torch.cuda.current_stream().wait_stream(self.side)
+        self._handles = []
+
+    def message_bytes(self) -> int:
+        return sum(f.numel() * f.element_size() for f in self.flat)

@@ -14,6 +14,22 @@ from ._lib import (BF16, F32, ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, EPI_DGEL
 Tensor = torch.Tensor
 LN_EPS = 1e-12                     # mm_modeling.py:159
 
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream:
+# entries are (kind, M, N, K, start_event, end_event).
+GEMM_PROFILE = None
+
+
+def _timed_call(kind, M, N, K, name, *args):
+    prof = GEMM_PROFILE
+    if prof is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    prof.append((kind, M, N, K, e0, e1))
+
 
 def dtype_code(t: Tensor) -> int:
     if t.dtype == torch.float32:
@@ -64,8 +80,8 @@ def gemm_tn(a: Tensor, b: Tensor, bias: Optional[Tensor] = None, epi: int = EPI_
     ldaux = _rows2d(aux)[2] if aux is not None else 0
     if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
         raise TypeError("gemm_tn: bias must be contiguous float32")
-    _lib.call("fcmf_gemm_tn", _p(a), lda, _p(b), ldb, _p(bias), _p(out), ldd, _p(aux), ldaux, M, N, K, epi,
-              dtype_code(a), engine, _stream())
+    _timed_call("tn", M, N, K, "fcmf_gemm_tn", _p(a), lda, _p(b), ldb, _p(bias), _p(out), ldd, _p(aux), ldaux, M, N, K,
+                epi, dtype_code(a), engine, _stream())
     return (out, aux) if (epi == EPI_GELU and want_aux) else out
 
 
@@ -82,8 +98,8 @@ def gemm_wgrad(dy: Tensor, x: Tensor, want_bias: bool = True, engine: int = ENGI
         accumulate = False
     if want_bias and db is None:
         db = torch.empty((N,), dtype=torch.float32, device=dy.device)
-    _lib.call("fcmf_gemm_wgrad", _p(dy), lddy, _p(x), ldx, _p(dw), _p(db) if want_bias else None, M, N, K,
-              1 if accumulate else 0, dtype_code(dy), engine, _stream())
+    _timed_call("wgrad", M, N, K, "fcmf_gemm_wgrad", _p(dy), lddy, _p(x), ldx, _p(dw), _p(db) if want_bias else None,
+                M, N, K, 1 if accumulate else 0, dtype_code(dy), engine, _stream())
     return dw, (db if want_bias else None)
 
 
@@ -177,6 +193,11 @@ def cast_to_f32(t: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------------------------------- attention
+def set_attn_engine(engine: int) -> None:
+    """ENGINE_AUTO (tcgen05 where supported), ENGINE_SIMT or ENGINE_TCGEN05 for subsequent attention launches."""
+    _lib.call("fcmf_set_attn_engine", engine)
+
+
 class SegSpec:
     """One query/key/value segment: `rows` rows per group taken from columns [col, col+heads*dh) of a 2-D tensor."""
     __slots__ = ("t", "col", "rows", "idx")

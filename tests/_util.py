@@ -43,3 +43,15 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 def golden_sample(t: torch.Tensor, stride: int) -> torch.Tensor:
     f = t.detach().reshape(-1).cpu()
     return f if f.numel() <= 4096 else f[::stride]
+
+
+def grad_scale(z) -> float:
+    """Largest |gradient| over all fusion parameters of a golden case: the floor for relative errors of gradients
+    that are identically zero in exact arithmetic (every attention KEY bias: adding a constant to all keys shifts a
+    softmax row uniformly), where both sides hold only rounding noise."""
+    return max(float(abs(z[k]).max()) for k in z.files if k.startswith("gsample/"))
+
+
+def rel_err_floor(a, b, floor: float) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))

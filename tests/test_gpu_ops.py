@@ -173,13 +173,25 @@ def attn_ref(qs, ks, vs, idxq, idxk, mask_add, mask_div, bias, heads, dh):
     return (p @ v).permute(0, 2, 1, 3).reshape(NP, q.shape[2], heads * dh)
 
 
-@pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("two_seg,use_bias,dh,heads", [(True, False, 64, 4), (False, True, 96, 8), (False, False, 64, 12)])
-def test_folded_attention_fwd_bwd(dtype, two_seg, use_bias, dh, heads):
+@pytest.mark.parametrize("dtype,engine", [(torch.float32, L.ENGINE_SIMT), (torch.bfloat16, L.ENGINE_SIMT),
+                                          (torch.bfloat16, L.ENGINE_TCGEN05)])
+@pytest.mark.parametrize("two_seg,use_bias,dh,heads,L1,L2", [
+    (True, False, 64, 4, 9, 4), (False, True, 96, 8, 7, 0), (False, False, 64, 12, 7, 0),
+    (True, False, 64, 2, 170, 4), (False, False, 64, 3, 49, 0), (False, False, 64, 1, 200, 0), (True, False, 64, 2, 130, 30)])
+def test_folded_attention_fwd_bwd(dtype, engine, two_seg, use_bias, dh, heads, L1, L2):
+    if engine == L.ENGINE_TCGEN05 and (use_bias or dh != 64 or L1 + L2 < 16):
+        pytest.skip("tcgen05 attention covers bf16, head_dim 64, no bias, L >= 16")
+    ops.set_attn_engine(engine)
+    try:
+        _attention_case(dtype, two_seg, use_bias, dh, heads, L1, L2)
+    finally:
+        ops.set_attn_engine(L.ENGINE_AUTO)
+
+
+def _attention_case(dtype, two_seg, use_bias, dh, heads, L1, L2):
     HD = heads * dh
     NI, A, B = 3, 2, 2
     BA, NP = B * A, B * A * NI
-    L1, L2 = (9, 4) if two_seg else (7, 0)
     p = torch.arange(NP, device=dev(), dtype=torch.int32)
     p2ba, p2bi = (p // NI).contiguous(), ((p // (A * NI)) * NI + p % NI).contiguous()
     ba2p = (torch.arange(BA, device=dev(), dtype=torch.int32).view(BA, 1) * NI + torch.arange(NI, device=dev(), dtype=torch.int32)).contiguous()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import golden_inputs, golden_sample, load_golden, rel_err
+from _util import golden_inputs, golden_sample, grad_scale, load_golden, rel_err, rel_err_floor
 from oracle import fcmf_oracle as O
 
 CASES = ["base_small", "base_roi7", "large_small", "base_cfg1_b1"]
@@ -29,7 +29,7 @@ def test_oracle_matches_reference_outputs(name):
     assert rel_err(got.reshape(-1), gold_dseq.reshape(-1)) < TOL
     for k, v in p.items():
         g = torch.from_numpy(z["gsample/" + k])
-        assert rel_err(golden_sample(v.grad, stride), g) < 5 * TOL, k
+        assert rel_err_floor(golden_sample(v.grad, stride), g, 1e-3 * grad_scale(z)) < 5 * TOL, k
         assert abs(v.grad.double().norm().item() - float(z["gnorm/" + k])) <= 5 * TOL * float(z["gnorm/" + k]) + 1e-12, k
 
 

@@ -7,10 +7,11 @@
 //   * "row operand"  (K-major):  rows = M or N index, the 64 columns are the reduction  (Q.K^T, dO.V^T, K.Q^T, V.dO^T)
 //   * "col operand"  (MN-major): rows = reduction index, the 64 columns are N            (P.V, dS.K, P^T.dO, dS^T.Q)
 // the SAME shared-memory image serves as either, only the descriptor differs.
-// Scores live in TMEM; each of the 128 threads owns one TMEM lane (= one query row, or one key row in the dK/dV
-// kernel), reads it with tcgen05.ld, does the softmax arithmetic in registers and writes the bf16 probabilities
-// back to shared memory as the A operand of the second contraction. Several CTAs share an SM (48-112 KB of shared
-// memory, 128-256 TMEM columns each), which is what overlaps one CTA's global loads with another's MMAs.
+// Scores live in TMEM; thread t of each warpgroup owns TMEM lane t (= one query row, or one key row in the dK/dV
+// kernel) and the two warpgroups split the 32-column chunks: tcgen05.ld, softmax arithmetic in registers, bf16
+// probabilities written back to shared memory as the A operand of the second contraction. Tiles are staged with
+// cp.async (16-byte, zero-fill for padded rows) so every global load of a tile is in flight at once; two CTAs share an
+// SM (<= 112 KB of shared memory, <= 256 TMEM columns each), which overlaps one CTA's loads with the other's MMAs.
 //
 // Reference semantics: BertCoAttention/BertSelfAttention.forward (mm_modeling.py:193-266): scale before the mask
 // add, additive -10000 mask on the keys, softmax over keys, context = P.V; backward = autograd of the same.
@@ -19,7 +20,7 @@
 
 namespace fcmf {
 
-constexpr int ATC_THREADS = 128;
+constexpr int ATC_THREADS = 256;                // 2 warpgroups: both own the 128 TMEM lanes, they split the column chunks
 constexpr int ATC_TILE = 128;                   // rows per CTA tile (UMMA M)
 constexpr int ATC_BLK = 64;                     // block width
 constexpr uint32_t ATC_TILE_BYTES = ATC_TILE * 128;   // 16 KB
@@ -105,13 +106,20 @@ __device__ __forceinline__ void block_mma_rc(uint32_t tmem_d, uint32_t a_tile, u
 // ------------------------------------------------------------------------------------------- tile staging
 __device__ __forceinline__ uint32_t swz(int r, int chunk) { return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)); }
 
+__device__ __forceinline__ void cp_async16(uint8_t* dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;                         // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // rows [row0, row0+tile_rows) of a segmented [L x 64] bf16 matrix of (problem p, head h) -> swizzled tile; rows >= L are 0
 __device__ __forceinline__ void stage_seg(uint8_t* tile, const SegDev (&s)[2], int p, int h, int row0, int tile_rows, int L) {
+  const bf16* safe = reinterpret_cast<const bf16*>(s[0].ptr);
   for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
     const int r = e >> 3, c = e & 7, gr = row0 + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gr < L) v = *reinterpret_cast<const uint4*>(seg_row<bf16>(s, p, gr, h, 64) + c * 8);
-    *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
+    const bool ok = gr < L;
+    cp_async16(tile + swz(r, c), ok ? seg_row<bf16>(s, p, gr, h, 64) + c * 8 : safe, ok);
   }
 }
 // same for a plain [NP*L, ld] activation (ctx / dctx)
@@ -119,9 +127,8 @@ __device__ __forceinline__ void stage_plain(uint8_t* tile, const bf16* base, int
                                             int tile_rows, int L) {
   for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
     const int r = e >> 3, c = e & 7, gr = row0 + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (gr < L) v = *reinterpret_cast<const uint4*>(base + (prow0 + gr) * ld + (int64_t)h * 64 + c * 8);
-    *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
+    const bool ok = gr < L;
+    cp_async16(tile + swz(r, c), ok ? base + (prow0 + gr) * ld + (int64_t)h * 64 + c * 8 : base, ok);
   }
 }
 // thread-owned row: write 32 consecutive bf16 (cols c0..c0+31 of a 64-col block) of row r into a swizzled tile
@@ -135,8 +142,20 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int r, int c0, const 
     *reinterpret_cast<uint4*>(tile + swz(r, (c0 >> 3) + g)) = w;
   }
 }
+// 32 fp32 TMEM values * scale -> 32 bf16 to global (64 contiguous bytes)
+__device__ __forceinline__ void store_out32(bf16* o, const uint32_t (&r)[32], float sc) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 w;
+    __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * sc, __uint_as_float(r[g * 8 + 2 * j + 1]) * sc);
+    *reinterpret_cast<uint4*>(o + g * 8) = w;
+  }
+}
 
-struct AtcShared {                               // lives at the start of dynamic smem (after 1024-alignment)
+struct AtcShared {
   uint64_t bar;
   uint32_t tmem;
 };
@@ -147,9 +166,9 @@ __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
 
 // ------------------------------------------------------------------------------------------- forward
 // smem: [Q tile 16K = P block 0 (Q is dead once S is in TMEM)][K blocks NKB*8K][V blocks NKB*8K][P blocks 1.. (NKB-1)*16K]
-//       [mask NKB*64 f32][AtcShared]
+//       [mask NKB*64 f32][red 2*2*128 f32][AtcShared]
 template <int NKB>
-__global__ void __launch_bounds__(ATC_THREADS)
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __restrict__ lse, int mtiles) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = align1k(raw);
@@ -158,11 +177,13 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
   uint8_t* Px = Vs + NKB * ATC_BLK_BYTES;
   float* msk = reinterpret_cast<float*>(Px + (NKB - 1) * ATC_TILE_BYTES);
-  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
+  float* red = msk + NKB * 64;                                  // [2 passes][2 groups][128 rows]
+  AtcShared* sh = reinterpret_cast<AtcShared*>(red + 512);
   constexpr uint32_t kCols = (NKB + 1) * 64 <= 128 ? 128 : ((NKB + 1) * 64 <= 256 ? 256 : 512);
   auto Pblk = [&](int b) -> uint8_t* { return b == 0 ? Qs : Px + (b - 1) * ATC_TILE_BYTES; };
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;     // TMEM lane / tile row owned by this thread
   const int mt = blockIdx.x % mtiles;
   const int ph = blockIdx.x / mtiles;
   const int p = ph / a.heads, h = ph % a.heads;
@@ -173,8 +194,10 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
   stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
   stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+  cp_async_commit();
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
   for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
+  cp_async_wait_all();
   a_fence_async();
   a_tc_before();
   __syncthreads();
@@ -190,18 +213,21 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   a_mbar_wait(&sh->bar, 0);
   a_tc_after();
 
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   float mx = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < NKB * 2; ++c) {
+  for (int c = grp; c < NKB * 2; c += 2) {
     uint32_t r[32];
     a_tmem_ld32(tS + lane_addr + c * 32, r);
 #pragma unroll
     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * a.scale + msk[c * 32 + j]);
   }
+  red[grp * 128 + trow] = mx;
+  __syncthreads();
+  mx = fmaxf(red[trow], red[128 + trow]);                       // finite: at least key 0 is real and its mask is finite
   float sum = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < NKB * 2; ++c) {
+  for (int c = grp; c < NKB * 2; c += 2) {
     uint32_t r[32];
     float v[32];
     a_tmem_ld32(tS + lane_addr + c * 32, r);
@@ -210,12 +236,14 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
       v[j] = __expf(__uint_as_float(r[j]) * a.scale + msk[c * 32 + j] - mx);
       sum += v[j];
     }
-    store_row32(Pblk(c >> 1), tid, (c & 1) * 32, v);
+    store_row32(Pblk(c >> 1), trow, (c & 1) * 32, v);
   }
+  red[256 + grp * 128 + trow] = sum;
   a_fence_async();
   a_tc_before();
   __syncthreads();
   a_tc_after();
+  sum = red[256 + trow] + red[256 + 128 + trow];
   if (tid == 0) {
     const int ksteps_total = (Lk + 15) >> 4;
 #pragma unroll
@@ -227,35 +255,22 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   }
   a_mbar_wait(&sh->bar, 1);
   a_tc_after();
-  const int row = row0 + tid;
-  const float inv = 1.0f / sum;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
+  const int row = row0 + trow;
+  {
     uint32_t r[32];
-    a_tmem_ld32(tO + lane_addr + c * 32, r);
-    if (row < Lq) {
-      bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + c * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 w;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * inv, __uint_as_float(r[g * 8 + 2 * j + 1]) * inv);
-        *reinterpret_cast<uint4*>(o + g * 8) = w;
-      }
-    }
+    a_tmem_ld32(tO + lane_addr + grp * 32, r);
+    if (row < Lq) store_out32(ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32, r, 1.0f / sum);
   }
-  if (row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = mx + __logf(sum);
+  if (grp == 0 && row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = mx + __logf(sum);
   a_tc_before();
   __syncthreads();
   if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
 }
 
 // ------------------------------------------------------------------------------------------- dQ (+ delta)
-// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
+// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][stat 128 float2][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
 template <int NKB>
-__global__ void __launch_bounds__(ATC_THREADS)
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const bf16* __restrict__ dctx, int64_t lddctx,
                   const float* __restrict__ lse, bf16* __restrict__ dq, float* __restrict__ delta, int mtiles) {
   extern __shared__ uint8_t raw[];
@@ -266,10 +281,12 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
   uint8_t* Ds = Vs + NKB * ATC_BLK_BYTES;
   float* msk = reinterpret_cast<float*>(Ds + ATC_TILE_BYTES);
-  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
+  float2* stat_s = reinterpret_cast<float2*>(msk + NKB * 64);   // (lse, delta) per tile row
+  AtcShared* sh = reinterpret_cast<AtcShared*>(stat_s + 128);
   constexpr uint32_t kCols = 256;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;
   const int mt = blockIdx.x % mtiles;
   const int ph = blockIdx.x / mtiles;
   const int p = ph / a.heads, h = ph % a.heads;
@@ -281,33 +298,47 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
   stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
   stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+  cp_async_commit();
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
   for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
 
-  // delta_i = dO_i . O_i  (thread-owned row, straight from global)
-  const int row = row0 + tid;
+  // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each
+  const int row = row0 + trow;
   const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
-  float dl = 0.f, l = 0.f;
-  if (row < Lq) {
-    const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64;
-    const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64;
+  {
+    float part = 0.f;
+    if (row < Lq) {
+      const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32;
+      const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64 + grp * 32;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      Vec16<bf16> x, y;
-      x.load(o + c * 8); y.load(g + c * 8);
+      for (int c = 0; c < 4; ++c) {
+        Vec16<bf16> x, y;
+        x.load(o + c * 8); y.load(g + c * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dl = fmaf(x.v[j], y.v[j], dl);
+        for (int j = 0; j < 8; ++j) part = fmaf(x.v[j], y.v[j], part);
+      }
     }
-    l = lse[stat];
-    delta[stat] = dl;
+    float* scratch = reinterpret_cast<float*>(Ds);               // dS tile is free until the first block
+    scratch[grp * 128 + trow] = part;
   }
+  cp_async_wait_all();
   a_fence_async();
   a_tc_before();
   __syncthreads();
   a_tc_after();
+  float dl = 0.f, l = 0.f;
+  {
+    const float* scratch = reinterpret_cast<const float*>(Ds);
+    dl = scratch[trow] + scratch[128 + trow];
+    if (row < Lq) {
+      l = lse[stat];
+      if (grp == 0) delta[stat] = dl;
+    }
+  }
+  __syncthreads();                                               // scratch (aliases dS) fully read before it is rewritten
   const uint32_t tm = sh->tmem;
   const uint32_t tS = tm, tP = tm + 64, tQ = tm + 128;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t parity = 0;
   const int nblk = (Lk + 63) >> 6;
 
@@ -318,20 +349,19 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
       block_mma_rr(tP, a_smem_u32(Gs), a_smem_u32(Vs + b * ATC_BLK_BYTES), false);      // dP_b = dO . V_b^T
       a_commit(&sh->bar);
     }
-    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // also orders the previous block's dQ MMA (reads Ds) before the rewrite below
+    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // also: the previous block's dQ MMA (reads dS) has retired
     a_tc_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t rs[32], rp[32];
       float v[32];
-      a_tmem_ld32(tS + lane_addr + c * 32, rs);
-      a_tmem_ld32(tP + lane_addr + c * 32, rp);
+      a_tmem_ld32(tS + lane_addr + grp * 32, rs);
+      a_tmem_ld32(tP + lane_addr + grp * 32, rp);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float pj = __expf(__uint_as_float(rs[j]) * a.scale + msk[b * 64 + c * 32 + j] - l);
+        const float pj = __expf(__uint_as_float(rs[j]) * a.scale + msk[b * 64 + grp * 32 + j] - l);
         v[j] = (row < Lq) ? pj * (__uint_as_float(rp[j]) - dl) : 0.f;
       }
-      store_row32(Ds, tid, c * 32, v);
+      store_row32(Ds, trow, grp * 32, v);
     }
     a_fence_async();
     a_tc_before();
@@ -345,22 +375,10 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   }
   a_mbar_wait(&sh->bar, parity);
   a_tc_after();
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
+  {
     uint32_t r[32];
-    a_tmem_ld32(tQ + lane_addr + c * 32, r);
-    if (row < Lq) {
-      bf16* o = dq + ((int64_t)p * Lq + row) * HD + (int64_t)h * 64 + c * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 w;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * a.scale, __uint_as_float(r[g * 8 + 2 * j + 1]) * a.scale);
-        *reinterpret_cast<uint4*>(o + g * 8) = w;
-      }
-    }
+    a_tmem_ld32(tQ + lane_addr + grp * 32, r);
+    if (row < Lq) store_out32(dq + ((int64_t)p * Lq + row) * HD + (int64_t)h * 64 + grp * 32, r, a.scale);
   }
   a_tc_before();
   __syncthreads();
@@ -368,110 +386,110 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
 }
 
 // ------------------------------------------------------------------------------------------- dK, dV
-// CTA tile = 128 KEY rows. smem: [K 16K][V 16K][Q NQB*8K][dO NQB*8K][P^T 16K][dS^T 16K][lse NQB*64][delta NQB*64][AtcShared]
+// CTA tile = 128 KEY rows; query blocks of 64 stream through a 2-stage ring (prefetched with cp.async).
+// smem: [K 16K][V 16K][ring 2 x (Q 8K | dO 8K)][P^T 16K][dS^T 16K][lse NQB*64][delta NQB*64][AtcShared]
 // TMEM: S^T 64 | dP^T 64 | dV 64 | dK 64
 template <int NQB>
-__global__ void __launch_bounds__(ATC_THREADS)
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, const float* __restrict__ lse,
                    const float* __restrict__ delta, bf16* __restrict__ dk, bf16* __restrict__ dv, int ktiles) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = align1k(raw);
   uint8_t* Ks = sm;
   uint8_t* Vs = Ks + ATC_TILE_BYTES;
-  uint8_t* Qs = Vs + ATC_TILE_BYTES;
-  uint8_t* Gs = Qs + NQB * ATC_BLK_BYTES;
-  uint8_t* Pt = Gs + NQB * ATC_BLK_BYTES;
+  uint8_t* ring = Vs + ATC_TILE_BYTES;                           // stage s: Q block at ring + s*16K, dO block 8K later
+  uint8_t* Pt = ring + 2 * ATC_TILE_BYTES;
   uint8_t* St = Pt + ATC_TILE_BYTES;
   float* ls = reinterpret_cast<float*>(St + ATC_TILE_BYTES);
   float* dls = ls + NQB * 64;
   AtcShared* sh = reinterpret_cast<AtcShared*>(dls + NQB * 64);
   constexpr uint32_t kCols = 256;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;
   const int kt = blockIdx.x % ktiles;
   const int ph = blockIdx.x / ktiles;
   const int p = ph / a.heads, h = ph % a.heads;
   const int Lq = a.Lq, Lk = a.Lk, key0 = kt * ATC_TILE, HD = a.heads * 64;
+  const int nblk = (Lq + 63) >> 6;
 
   if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
   if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
   stage_seg(Ks, a.k, p, h, key0, ATC_TILE, Lk);
   stage_seg(Vs, a.v, p, h, key0, ATC_TILE, Lk);
-  stage_seg(Qs, a.q, p, h, 0, NQB * 64, Lq);
-  stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, 0, NQB * 64, Lq);
+  stage_seg(ring, a.q, p, h, 0, 64, Lq);
+  stage_plain(ring + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, 0, 64, Lq);
+  cp_async_commit();
   const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
   for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
     ls[i] = i < Lq ? lse[stat0 + i] : INFINITY;          // exp(s - inf) = 0 for the padded queries
     dls[i] = i < Lq ? delta[stat0 + i] : 0.f;
   }
-  const int key = key0 + tid;
+  const int key = key0 + trow;
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
   const float mk = (key < Lk && madd) ? madd[key] : 0.f;
+  cp_async_wait_all();
   a_fence_async();
   a_tc_before();
   __syncthreads();
   a_tc_after();
   const uint32_t tm = sh->tmem;
   const uint32_t tS = tm, tP = tm + 64, tV = tm + 128, tK = tm + 192;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t parity = 0;
-  const int nblk = (Lq + 63) >> 6;
 
 #pragma unroll 1
   for (int b = 0; b < nblk; ++b) {
+    uint8_t* Qb = ring + (b & 1) * ATC_TILE_BYTES;
+    uint8_t* Gb = Qb + ATC_BLK_BYTES;
     if (tid == 0) {
-      block_mma_rr(tS, a_smem_u32(Ks), a_smem_u32(Qs + b * ATC_BLK_BYTES), false);      // S^T_b  = K . Q_b^T
-      block_mma_rr(tP, a_smem_u32(Vs), a_smem_u32(Gs + b * ATC_BLK_BYTES), false);      // dP^T_b = V . dO_b^T
+      block_mma_rr(tS, a_smem_u32(Ks), a_smem_u32(Qb), false);                          // S^T_b  = K . Q_b^T
+      block_mma_rr(tP, a_smem_u32(Vs), a_smem_u32(Gb), false);                          // dP^T_b = V . dO_b^T
       a_commit(&sh->bar);
     }
-    a_mbar_wait(&sh->bar, parity); parity ^= 1;
+    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // every earlier MMA has retired: the other ring stage and P^T/dS^T are free
     a_tc_after();
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    if (b + 1 < nblk) {                                // prefetch the next query block while this one is processed
+      uint8_t* Qn = ring + ((b + 1) & 1) * ATC_TILE_BYTES;
+      stage_seg(Qn, a.q, p, h, (b + 1) * 64, 64, Lq);
+      stage_plain(Qn + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, (b + 1) * 64, 64, Lq);
+    }
+    cp_async_commit();
+    {
       uint32_t rs[32], rp[32];
       float pv[32], dsv[32];
-      a_tmem_ld32(tS + lane_addr + c * 32, rs);
-      a_tmem_ld32(tP + lane_addr + c * 32, rp);
+      a_tmem_ld32(tS + lane_addr + grp * 32, rs);
+      a_tmem_ld32(tP + lane_addr + grp * 32, rp);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int qi = b * 64 + c * 32 + j;
+        const int qi = b * 64 + grp * 32 + j;
         const float pj = (key < Lk) ? __expf(__uint_as_float(rs[j]) * a.scale + mk - ls[qi]) : 0.f;
         pv[j] = pj;
         dsv[j] = pj * (__uint_as_float(rp[j]) - dls[qi]);
       }
-      store_row32(Pt, tid, c * 32, pv);
-      store_row32(St, tid, c * 32, dsv);
+      store_row32(Pt, trow, grp * 32, pv);
+      store_row32(St, trow, grp * 32, dsv);
     }
+    cp_async_wait_all();
     a_fence_async();
     a_tc_before();
     __syncthreads();
     a_tc_after();
     if (tid == 0) {
       const int ks = min(4, ((Lq + 15) >> 4) - b * 4);
-      block_mma_rc(tV, a_smem_u32(Pt), a_smem_u32(Gs + b * ATC_BLK_BYTES), b > 0, ks);  // dV += P^T_b . dO_b
-      block_mma_rc(tK, a_smem_u32(St), a_smem_u32(Qs + b * ATC_BLK_BYTES), b > 0, ks);  // dK += dS^T_b . Q_b
+      block_mma_rc(tV, a_smem_u32(Pt), a_smem_u32(Gb), b > 0, ks);                      // dV += P^T_b . dO_b
+      block_mma_rc(tK, a_smem_u32(St), a_smem_u32(Qb), b > 0, ks);                      // dK += dS^T_b . Q_b
       if (b == nblk - 1) a_commit(&sh->bar);
     }
   }
   a_mbar_wait(&sh->bar, parity);
   a_tc_after();
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = grp; c < 4; c += 2) {                   // chunks 0,1 = dV columns, 2,3 = dK columns
     uint32_t r[32];
     a_tmem_ld32((c < 2 ? tV : tK) + lane_addr + (c & 1) * 32, r);
-    if (key < Lk) {
-      const float sc = c < 2 ? 1.0f : a.scale;
-      bf16* o = (c < 2 ? dv : dk) + ((int64_t)p * Lk + key) * HD + (int64_t)h * 64 + (c & 1) * 32;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 w;
-        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * sc, __uint_as_float(r[g * 8 + 2 * j + 1]) * sc);
-        *reinterpret_cast<uint4*>(o + g * 8) = w;
-      }
-    }
+    if (key < Lk)
+      store_out32((c < 2 ? dv : dk) + ((int64_t)p * Lk + key) * HD + (int64_t)h * 64 + (c & 1) * 32, r, c < 2 ? 1.0f : a.scale);
   }
   a_tc_before();
   __syncthreads();
@@ -507,7 +525,7 @@ int attn_tc_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStre
   const int nkb = (a.Lk + 63) / 64, mtiles = (a.Lq + 127) / 128;
   const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
 #define CALL(NB)                                                                                              \
-  const size_t smem = 1024 + (size_t)NB * (2 * ATC_BLK_BYTES + ATC_TILE_BYTES + 256) + 64;                   \
+  const size_t smem = 1024 + (size_t)NB * (2 * ATC_BLK_BYTES + ATC_TILE_BYTES + 256) + 2048 + 64;            \
   if (int r = set_smem_tc(attn_tc_fwd_kernel<NB>, smem)) return r;                                            \
   attn_tc_fwd_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (bf16*)ctx, ldctx, lse, mtiles);
   ATC_DISPATCH(nkb, CALL)
@@ -523,7 +541,7 @@ int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
   {
     const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
 #define CALL(NB)                                                                                              \
-    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 64;             \
+    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 1024 + 64;      \
     if (int r = set_smem_tc(attn_tc_dq_kernel<NB>, smem)) return r;                                           \
     attn_tc_dq_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse, (bf16*)dq, delta, mtiles);
     ATC_DISPATCH(nkb, CALL)
@@ -533,7 +551,7 @@ int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
   {
     const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * ktiles);
 #define CALL(NB)                                                                                              \
-    const size_t smem = 1024 + 4 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 512) + 64;             \
+    const size_t smem = 1024 + 6 * ATC_TILE_BYTES + (size_t)NB * 512 + 64;                                   \
     if (int r = set_smem_tc(attn_tc_dkv_kernel<NB>, smem)) return r;                                          \
     attn_tc_dkv_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)dctx, lddctx, lse, delta, (bf16*)dk, (bf16*)dv, ktiles);
     ATC_DISPATCH(nqb, CALL)

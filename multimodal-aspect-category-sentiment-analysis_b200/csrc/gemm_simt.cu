@@ -83,10 +83,58 @@ gemm_simt_kernel(const TIn* __restrict__ A, int64_t sam, int64_t sak,
   }
 }
 
-// db[n] (+)= sum_m dY[m, n]
+// db[n] (+)= sum_m dY[m, n].  HBM-bound: each warp reads whole 512-byte (bf16) / 512-byte (f32) row segments with
+// 16-byte vector loads, 8 warps of a block take interleaved rows, partial sums are combined in shared memory and one
+// atomic per column per block goes to global.
+constexpr int CS_WARPS = 8;
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, float* __restrict__ db, int64_t M, int64_t N,
-                              int64_t rows_per_block) {
+__global__ void __launch_bounds__(CS_WARPS * 32)
+colsum_kernel(const T* __restrict__ dY, int64_t ld, float* __restrict__ db, int64_t M, int64_t N, int64_t rows_per_block) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[CS_WARPS][32 * V];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n0 = ((int64_t)blockIdx.x * 32 + lane) * V;
+  const int64_t m_lo = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t m_hi = m_lo + rows_per_block < M ? m_lo + rows_per_block : M;
+  float acc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  if (n0 < N) {                                           // N % V == 0 is checked on the host
+    int64_t m = m_lo + warp;
+    for (; m + 3 * CS_WARPS < m_hi; m += 4 * CS_WARPS) {  // 4 independent 16-byte loads in flight per thread
+      Vec16<T> v0, v1, v2, v3;
+      v0.load(dY + m * ld + n0);
+      v1.load(dY + (m + CS_WARPS) * ld + n0);
+      v2.load(dY + (m + 2 * CS_WARPS) * ld + n0);
+      v3.load(dY + (m + 3 * CS_WARPS) * ld + n0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += (v0.v[j] + v1.v[j]) + (v2.v[j] + v3.v[j]);
+    }
+    for (; m < m_hi; m += CS_WARPS) {
+      Vec16<T> v0;
+      v0.load(dY + m * ld + n0);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] += v0.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[warp][lane * V + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += blockDim.x) {
+    const int64_t n = (int64_t)blockIdx.x * 32 * V + c;
+    if (n < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < CS_WARPS; ++w) s += red[w][c];
+      atomicAdd(db + n, s);
+    }
+  }
+}
+
+// scalar fallback for column counts / alignments the vector kernel cannot take
+template <typename T>
+__global__ void colsum_scalar_kernel(const T* __restrict__ dY, int64_t ld, float* __restrict__ db, int64_t M, int64_t N,
+                                     int64_t rows_per_block) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int64_t m_lo = (int64_t)blockIdx.y * rows_per_block;
@@ -98,14 +146,18 @@ __global__ void colsum_kernel(const T* __restrict__ dY, int64_t ld, float* __res
 
 template <typename T>
 int colsum_launch(const T* dY, int64_t ld, float* db, int64_t M, int64_t N, int accumulate, cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
   if (!accumulate) FCMF_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
   if (M == 0) return 0;
-  int64_t want_blocks_y = (4LL * sm_count() * 128 + N - 1) / N;       // ~4 waves of 128-thread blocks
-  if (want_blocks_y < 1) want_blocks_y = 1;
-  int64_t rows = (M + want_blocks_y - 1) / want_blocks_y;
-  if (rows < 32) rows = 32;
-  dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + rows - 1) / rows));
-  colsum_kernel<T><<<grid, 128, 0, st>>>(dY, ld, db, M, N, rows);
+  const bool vec = (N % V == 0) && (ld % V == 0) && ((reinterpret_cast<uintptr_t>(dY) & 15u) == 0);
+  const int64_t col_blocks = vec ? (N + 32 * V - 1) / (32 * V) : (N + 127) / 128;
+  int64_t want_y = (4LL * sm_count() + col_blocks - 1) / col_blocks;       // ~4 blocks per SM in total
+  if (want_y < 1) want_y = 1;
+  int64_t rows = (M + want_y - 1) / want_y;
+  if (rows < 64) rows = 64;
+  dim3 grid((unsigned)col_blocks, (unsigned)((M + rows - 1) / rows));
+  if (vec) colsum_kernel<T><<<grid, CS_WARPS * 32, 0, st>>>(dY, ld, db, M, N, rows);
+  else colsum_scalar_kernel<T><<<grid, 128, 0, st>>>(dY, ld, db, M, N, rows);
   FCMF_LAUNCH_OK();
   return 0;
 }

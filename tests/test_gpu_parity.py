@@ -55,7 +55,10 @@ def test_fp32_matches_reference_golden(name, rows):
         # d/dz log(z) = 1/z with z = WG.emb + b as small as 1e-6 amplifies fp32 summation-order noise of z (the
         # reference's own rounding included) by up to 1e6: the geometry weights' gradients are ill-conditioned.
         tol = 3e-3 if ".WGs." in k else TOL
-        assert rel_err_floor(golden_sample(v.grad, stride), g, floor) < tol, k
+        # attention KEY biases have an exactly-zero true gradient (softmax shift invariance): both sides hold only the
+        # rounding residue of a long cancelling sum, so they are compared on the scale of the real gradients.
+        zero_grad = k.endswith("key.bias") or k.endswith("box_head.linears.1.bias")
+        assert rel_err_floor(golden_sample(v.grad, stride), g, 100 * floor if zero_grad else floor) < tol, k
 
 
 def test_per_aspect_forward_equals_folded_launch():

@@ -289,6 +289,16 @@ def main():
                         "(events recorded on the launching stream around each launch; includes the bias column-sum that "
                         "rides with each weight-gradient call)"}
 
+    if os.environ.get("FCMF_BENCH_GEMM_TABLE") and rank == 0:        # per-shape GEMM table on stderr (diagnostics)
+        table = {}
+        for (kind, M, N, K, a, b) in timed_entries:
+            t = table.setdefault((kind, M, N, K), [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        for (kind, M, N, K), (n, t) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {kind:5s} M={M:7d} N={N:5d} K={K:7d} x{n // args.steps:2d}/step {t / n:8.3f} ms  "
+                  f"{2.0 * M * N * K / (t / n * 1e-3) / 1e12:7.1f} TFLOP/s", file=sys.stderr)
+
     # ---- end to end: host (pinned) inputs copied H2D and logits+loss read back D2H inside the timed region ---------
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e, _ = timed(lambda: e2e_step(args.rows), e2e_steps, 2)

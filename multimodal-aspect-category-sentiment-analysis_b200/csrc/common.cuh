@@ -101,4 +101,29 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {       // d/dx [x * Phi
   return cdf + x * pdf;
 }
 
+// Epilogue-rate versions for the bf16 tensor-core GEMM (the erf-GELU epilogue is issue-bound on 4..8 epilogue warps):
+// erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 -- three orders below bf16 resolution -- with one MUFU.RCP and
+// one MUFU.EX2 instead of erff's ~25-instruction polynomial. exp(-z^2) with z = x/sqrt(2) is also the Gaussian density
+// the derivative needs, so gelu' costs no second exponential.
+__device__ __forceinline__ void erf_as_parts(float x, float& erf_z, float& gauss) {
+  const float z = x * 0.70710678118654752440f, az = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  gauss = __expf(-az * az);                               // exp(-x^2 / 2)
+  erf_z = copysignf(fmaf(-p * t, gauss, 1.0f), z);
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  float e, g;
+  erf_as_parts(x, e, g);
+  return x * 0.5f * (1.0f + e);
+}
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+  float e, g;
+  erf_as_parts(x, e, g);
+  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + e));
+}
+
 }  // namespace fcmf

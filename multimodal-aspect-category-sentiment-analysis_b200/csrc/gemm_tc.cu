@@ -17,6 +17,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace fcmf {
 
@@ -24,8 +25,8 @@ namespace fcmf {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;                 // 6 warps
-constexpr int TC_EPI_WARP0 = 2;                 // warps 2..5
+constexpr int TC_THREADS = 320;                 // 10 warps: TMA, MMA, 8 epilogue
+constexpr int TC_EPI_WARP0 = 2;                 // warps 2..9: two per TMEM lane quarter, they split the column chunks
 constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024; // ring + barriers, leaves room under the 227 KB limit
 
 template <int BN> struct TcCfg {
@@ -147,6 +148,68 @@ struct TcParams {
   int f32_mode;                                // 0 = bf16 epilogue, 1 = fp32 store, 2 = fp32 atomic add
 };
 
+// One thread's 32 consecutive accumulator columns of output row m, starting at column n0: bias / activation / store.
+__device__ __forceinline__ void epilogue_store(const TcParams& P, int64_t m, int64_t n0, const uint32_t (&r)[32]) {
+  if (P.f32_mode == 0) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    const int ncols = (int)min((int64_t)32, P.Ng - n0);       // multiple of 8 (checked on the host)
+    if (P.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(P.bias + n0 + j);
+    }
+    if (P.epi == FCMF_EPI_GELU) {
+      if (P.aux) {
+        bf16* ap = P.aux + m * P.ldaux + n0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+          uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+          *reinterpret_cast<uint4*>(ap + g * 8) = w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+    } else if (P.epi == FCMF_EPI_TANH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+    } else if (P.epi == FCMF_EPI_DGELU) {
+      const bf16* ap = P.aux + m * P.ldaux + n0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+        const uint4 w = *reinterpret_cast<const uint4*>(ap + g * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v[g * 8 + 2 * j] *= gelu_erf_grad_fast(f.x);
+          v[g * 8 + 2 * j + 1] *= gelu_erf_grad_fast(f.y);
+        }
+      }
+    }
+    bf16* dp = P.D + m * P.ldd + n0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+      uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+      *reinterpret_cast<uint4*>(dp + g * 8) = w;
+    }
+  } else {
+    float* dp = P.Df + m * P.lddf + n0;
+    const int ncols = (int)min((int64_t)32, P.Ng - n0);
+    if (P.f32_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
@@ -166,7 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -249,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================================================================== epilogue (4 warps, one lane quarter each)
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, half = (warp - TC_EPI_WARP0) >> 2;
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int split = (int)(u % P.splits);
@@ -263,71 +326,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m = (int64_t)m_blk * TC_BM + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c * 32, r);
         tmem_ld_wait();
         const int64_t n0 = (int64_t)n_blk * BN + c * 32;
-        if (m < P.Mg && n0 < P.Ng && has_work) {
-          if (P.f32_mode == 0) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            const int ncols = (int)min((int64_t)32, P.Ng - n0);       // multiple of 8 (checked on the host)
-            if (P.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(P.bias + n0 + j);
-            }
-            if (P.epi == FCMF_EPI_GELU) {
-              if (P.aux) {
-                bf16* ap = P.aux + m * P.ldaux + n0;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
-                  uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-                  *reinterpret_cast<uint4*>(ap + g * 8) = w;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            } else if (P.epi == FCMF_EPI_TANH) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-            } else if (P.epi == FCMF_EPI_DGELU) {
-              const bf16* ap = P.aux + m * P.ldaux + n0;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
-                const uint4 w = *reinterpret_cast<const uint4*>(ap + g * 8);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(h[j]);
-                  v[g * 8 + 2 * j] *= gelu_erf_grad(f.x);
-                  v[g * 8 + 2 * j + 1] *= gelu_erf_grad(f.y);
-                }
-              }
-            }
-            bf16* dp = P.D + m * P.ldd + n0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
-              uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-              *reinterpret_cast<uint4*>(dp + g * 8) = w;
-            }
-          } else {
-            float* dp = P.Df + m * P.lddf + n0;
-            const int ncols = (int)min((int64_t)32, P.Ng - n0);
-            if (P.f32_mode == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
-            }
-          }
-        }
+        if (m < P.Mg && n0 < P.Ng && has_work) epilogue_store(P, m, n0, r);
       }
       tc_fence_before();
       __syncwarp();
@@ -338,6 +342,194 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------------- 2-CTA (cta_group::2) kernel
+// A CTA pair (cluster of 2 on one TPC) owns a 256 x 256 output tile: each CTA stages its own 128 rows of A and its
+// own 128-row half of B (32 KB per stage instead of 48 KB for the same MMA work), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes 128 accumulator lanes into each
+// CTA's TMEM. This halves the L2 -> SM operand traffic per FLOP, which is what bounds the 1-CTA kernel.
+constexpr int TC2_BN = 256;
+constexpr int TC2_STAGE_A = TC_BM * TC_BK * 2;        // 16 KB: this CTA's 128 rows of A
+constexpr int TC2_STAGE_B = 128 * TC_BK * 2;          // 16 KB: this CTA's half of the 256 B rows
+constexpr int TC2_STAGE = TC2_STAGE_A + TC2_STAGE_B;
+constexpr int TC2_STAGES = 6;
+constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE + 1024 + 256;
+constexpr uint32_t TC2_PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & TC2_PEER_MASK), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_out, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {      // arrives on `bar` at the same offset in BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE);
+  uint64_t* empty_bar = full_bar + TC2_STAGES;
+  uint64_t* tfull_bar = empty_bar + TC2_STAGES;           // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                   // [2], only the leader copy is used (16 arrivals: 8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;      // tiles are 256 x 256 here
+  const int kb_per_split = (P.k_blocks + P.splits - 1) / P.splits;
+  const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t u = cluster_id; u < units; u += n_clusters) {
+        const int split = (int)(u % P.splits);
+        const int64_t tile = u / P.splits;
+        const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(P.k_blocks, kb0 + kb_per_split);
+        const int m0 = m_blk * 256 + (int)rank * 128, n0 = n_blk * 256 + (int)rank * 128;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * TC2_STAGE;
+          uint8_t* sb = sa + TC2_STAGE_A;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * TC2_STAGE);      // bytes of BOTH CTAs land on the leader's barrier
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * TC_BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * (TC_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, kb * TC_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * TC_BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sb + c * (TC_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, kb * TC_BK);
+          }
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(256, TC2_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t a_lbo = A_MN ? TC_BK * 128 : 16, b_lbo = B_MN ? TC_BK * 128 : 16;
+      constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
+      constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int64_t u = cluster_id; u < units; u += n_clusters, ++it) {
+        const int split = (int)(u % P.splits);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(P.k_blocks, kb0 + kb_per_split);
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * TC2_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * TC2_STAGE);
+          const uint32_t sb = sa + TC2_STAGE_A;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_f16_2sm(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - TC_EPI_WARP0) >> 2;
+    uint32_t it = 0;
+    for (int64_t u = cluster_id; u < units; u += n_clusters, ++it) {
+      const int split = (int)(u % P.splits);
+      const int64_t tile = u / P.splits;
+      const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
+      const int kb0 = split * kb_per_split;
+      const bool has_work = kb0 < P.k_blocks;
+      const uint32_t buf = it & 1, use = it >> 1;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_blk * 256 + (int64_t)rank * 128 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC2_BN;
+#pragma unroll 1
+      for (int c = half; c < TC2_BN / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int64_t n0 = (int64_t)n_blk * TC2_BN + c * 32;
+        if (m < P.Mg && n0 < P.Ng && has_work) epilogue_store(P, m, n0, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(&tempty_bar[buf], 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // the peer's smem/TMEM/barriers stay valid until both are done
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -410,6 +602,31 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& 
   return 0;
 }
 
+// FCMF_GEMM_2CTA=0 disables the cta_group::2 kernel (debug / A-B measurements)
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FCMF_GEMM_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, cudaStream_t st) {
+  auto kern = gemm_tc2_kernel<A_MN, B_MN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  FCMF_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    FCMF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;
+  const int64_t pairs = sm_count() / 2;
+  const int grid = 2 * (int)(units < pairs ? units : pairs);
+  kern<<<grid, TC_THREADS, TC2_SMEM, st>>>(ta, tb, P);
+  FCMF_LAUNCH_OK();
+  return 0;
+}
+
 int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, void* D, int64_t ldd,
                void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi, cudaStream_t st) {
   TcParams P{};
@@ -418,6 +635,14 @@ int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const flo
   P.k_blocks = (int)((K + TC_BK - 1) / TC_BK);
   P.splits = 1;
   P.bias = bias; P.D = (bf16*)D; P.ldd = ldd; P.aux = (bf16*)aux; P.ldaux = ldaux; P.epi = epi; P.f32_mode = 0;
+  if (use_2cta() && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= sm_count() / 2) {
+    P.m_tiles = (int)((M + 255) / 256);
+    P.n_tiles = (int)(N / 256);
+    CUtensorMap ta2, tb2;
+    if (int r = make_map(&ta2, A, M, K, lda, TC_BK, 128)) return r;
+    if (int r = make_map(&tb2, B, N, K, ldb, TC_BK, 128)) return r;
+    return launch2<false, false>(ta2, tb2, P, st);
+  }
   // 256-wide tiles unless that leaves SMs idle
   const int64_t tiles256 = (int64_t)P.m_tiles * ((N + 255) / 256);
   const bool wide = (N % 256 == 0 || N > 1024) && tiles256 >= sm_count();
@@ -440,6 +665,23 @@ int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, floa
   P.Mg = N; P.Ng = K; P.Kg = M;
   P.m_tiles = (int)((N + TC_BM - 1) / TC_BM);
   P.k_blocks = (int)((M + TC_BK - 1) / TC_BK);
+  if (use_2cta() && N % 256 == 0 && K % 256 == 0) {
+    P.m_tiles = (int)(N / 256);
+    P.n_tiles = (int)(K / 256);
+    const int64_t tiles2 = (int64_t)P.m_tiles * P.n_tiles, pairs = sm_count() / 2;
+    int splits = (int)((pairs + tiles2 - 1) / tiles2);
+    if (splits > P.k_blocks) splits = P.k_blocks;
+    if (splits < 1) splits = 1;
+    while (splits > 1 && (int64_t)(splits - 1) * ((P.k_blocks + splits - 1) / splits) >= P.k_blocks) --splits;
+    P.splits = splits;
+    P.Df = dW; P.lddf = K; P.epi = FCMF_EPI_NONE;
+    P.f32_mode = (splits == 1 && !accumulate) ? 1 : 2;
+    if (P.f32_mode == 2 && !accumulate) FCMF_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st));
+    CUtensorMap ta2, tb2;
+    if (int r = make_map(&ta2, dY, M, N, lddy, 64, TC_BK)) return r;
+    if (int r = make_map(&tb2, X, M, K, ldx, 64, TC_BK)) return r;
+    return launch2<true, true>(ta2, tb2, P, st);
+  }
   const bool wide = (K % 256 == 0);
   const int bn = wide ? 256 : 128;
   P.n_tiles = (int)((K + bn - 1) / bn);

@@ -101,29 +101,45 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {       // d/dx [x * Phi
   return cdf + x * pdf;
 }
 
-// Epilogue-rate versions for the bf16 tensor-core GEMM (the erf-GELU epilogue is issue-bound on 4..8 epilogue warps):
-// erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 -- three orders below bf16 resolution -- with one MUFU.RCP and
-// one MUFU.EX2 instead of erff's ~25-instruction polynomial. exp(-z^2) with z = x/sqrt(2) is also the Gaussian density
-// the derivative needs, so gelu' costs no second exponential.
-__device__ __forceinline__ void erf_as_parts(float x, float& erf_z, float& gauss) {
-  const float z = x * 0.70710678118654752440f, az = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+// Epilogue-rate versions for the bf16 tensor-core GEMM (the erf-GELU epilogue is issue-bound on the 8 epilogue warps:
+// ncu showed 46 warp-instructions per element with erff / __frcp_rn slow-path calls, 24 % tensor-pipe activity).
+// erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 -- three orders below bf16 resolution -- with exactly one
+// MUFU.RCP and one MUFU.EX2 (raw approx instructions: no special-case subroutine, no divergence). exp(-z^2) with
+// z = x/sqrt(2) is also the Gaussian density the derivative needs, so gelu' costs no second exponential.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tanh_approx(float x) {          // MUFU.TANH, rel. error ~2^-11 (< bf16 rounding)
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void erf_as_parts(float x, float& erf_abs, float& gauss) {   // erf(|x|/sqrt2), exp(-x^2/2)
+  const float az = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  gauss = __expf(-az * az);                               // exp(-x^2 / 2)
-  erf_z = copysignf(fmaf(-p * t, gauss, 1.0f), z);
+  gauss = ex2_approx(az * az * -1.44269504088896340736f);
+  erf_abs = fmaf(-p * t, gauss, 1.0f);
 }
-__device__ __forceinline__ float gelu_erf_fast(float x) {
+__device__ __forceinline__ float gelu_erf_fast(float x) {       // x * Phi(x);  Phi(x) = 0.5 + 0.5 * sign(x) * erf(|x|/sqrt2)
   float e, g;
   erf_as_parts(x, e, g);
-  return x * 0.5f * (1.0f + e);
+  return fmaf(0.5f * fabsf(x), e, 0.5f * x);                    // 0.5x + 0.5|x| erf(|z|)  (sign folded into |x|)
 }
-__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {  // Phi(x) + x * phi(x)
   float e, g;
   erf_as_parts(x, e, g);
-  return fmaf(x * 0.39894228040143267794f, g, 0.5f * (1.0f + e));
+  return fmaf(x * 0.39894228040143267794f, g, fmaf(copysignf(0.5f, x), e, 0.5f));
 }
 
 }  // namespace fcmf

@@ -1,14 +1,21 @@
 // tcgen05 / TMEM / TMA GEMM engine for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
 //
-//   * persistent, warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and
-//     TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each);
-//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a kStages-deep shared-memory ring,
-//     consumed by tcgen05.mma.cta_group::1.kind::f16 straight from shared memory through matrix descriptors;
-//   * the 128 x BN fp32 accumulator lives in TMEM, double-buffered so the epilogue of tile i overlaps the
-//     main loop of tile i+1; epilogue = tcgen05.ld -> bias / erf-GELU / tanh / dGELU -> global;
-//   * both operand majors: K-major (forward and input-gradient GEMMs) and MN-major (weight-gradient GEMM,
-//     where the reduction runs over the rows of two row-major activation matrices), split along the
-//     reduction with fp32 atomics for the weight gradient.
+//   * persistent, warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and TMEM
+//     owner, warps 2..9 = epilogue (two warps per TMEM lane quarter);
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a shared-memory ring and consumed by
+//     tcgen05.mma.kind::f16 straight from shared memory through matrix descriptors;
+//   * accumulators live in TMEM, double-buffered: the epilogue of tile i overlaps the main loop of tile i+1;
+//   * bf16 epilogue: tcgen05.ld -> bias / erf-GELU / tanh / dGELU in registers -> 128-byte-swizzled shared-memory
+//     slab of 128 rows x 64 columns -> ONE TMA store per slab (cp.async.bulk.tensor store). A thread owns a TMEM lane,
+//     i.e. an output ROW, so direct global stores would issue 16-byte requests to 32 different rows per instruction
+//     (measured: the L2 request rate, not DRAM, bounded the N=3072/K=768 GEMMs at 430 TFLOP/s); the TMA store moves
+//     whole 128-byte lines and also clips the M/N tails. The dGELU epilogue's auxiliary input comes in the same way
+//     (TMA load of the matching slab);
+//   * both operand majors: K-major (forward and input-gradient GEMMs) and MN-major (weight-gradient GEMM, whose
+//     reduction runs over the rows of two row-major activation matrices), split along the reduction with fp32
+//     atomics for the weight gradient;
+//   * two kernels: a CTA-pair kernel (cta_group::2, 256 x 256 tile per pair, half the L2->SM operand traffic per
+//     FLOP) for large problems and a single-CTA kernel (128 x 256 / 128 x 128) for everything else.
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables
 // (same bit layout as cute::UMMA::SmemDescriptor / InstrDescriptor).
@@ -26,16 +33,18 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 320;                 // 10 warps: TMA, MMA, 8 epilogue
-constexpr int TC_EPI_WARP0 = 2;                 // warps 2..9: two per TMEM lane quarter, they split the column chunks
-constexpr uint32_t TC_SMEM_BUDGET = 200 * 1024; // ring + barriers, leaves room under the 227 KB limit
+constexpr int TC_EPI_WARP0 = 2;                 // warps 2..9: two per TMEM lane quarter, one 32-column half of a slab each
+constexpr int TC_SLAB_BYTES = TC_BM * 128;      // 128 rows x 64 bf16 columns
+constexpr int TC_EPI_SMEM = 4 * TC_SLAB_BYTES;  // 2 buffers x (D slab + aux slab)
+constexpr int TC_CTRL_BYTES = 512;              // barriers + TMEM slot
 
 template <int BN> struct TcCfg {
   static constexpr int kStageA = TC_BM * TC_BK * 2;                 // 16 KB
   static constexpr int kStageB = BN * TC_BK * 2;                    // 16 / 32 KB
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (int)(TC_SMEM_BUDGET / kStageBytes) > 8 ? 8 : (int)(TC_SMEM_BUDGET / kStageBytes);
+  static constexpr int kStages = BN == 256 ? 3 : 4;                 // 144 / 128 KB of operand ring
   static constexpr int kTmemCols = 2 * BN;                          // double-buffered accumulator (256 / 512)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + TC_EPI_SMEM + 1024 /*align*/ + TC_CTRL_BYTES;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -75,6 +84,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
   asm volatile(
@@ -82,6 +92,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -134,52 +153,117 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ------------------------------------------------------------------------------------------- kernel
+// ------------------------------------------------------------------------------------------- parameters
 struct TcParams {
   // logical GEMM: D[Mg, Ng] = sum_k A(m,k) B(n,k), k < Kg
   int64_t Mg, Ng, Kg;
   int m_tiles, n_tiles, k_blocks, splits;      // work unit = (tile, split)
-  // epilogue
   const float* bias;
-  bf16* D; int64_t ldd;
-  bf16* aux; int64_t ldaux;
   float* Df; int64_t lddf;                     // fp32 output (weight gradient)
   int epi;
-  int f32_mode;                                // 0 = bf16 epilogue, 1 = fp32 store, 2 = fp32 atomic add
+  int f32_mode;                                // 0 = bf16 epilogue through TMA stores, 1 = fp32 store, 2 = fp32 atomic add
+  int has_aux;                                 // bf16 mode: aux tensor map is valid (GELU: output, dGELU: input)
 };
 
-// One thread's 32 consecutive accumulator columns of output row m, starting at column n0: bias / activation / store.
-__device__ __forceinline__ void epilogue_store(const TcParams& P, int64_t m, int64_t n0, const uint32_t (&r)[32]) {
-  if (P.f32_mode == 0) {
+struct EpiCtx {                                // per-thread view of the epilogue's shared resources
+  uint8_t* stage;                              // 4 slabs: [buf][D | aux]
+  uint64_t* xbar;                              // [2] aux-slab-landed barriers (dGELU)
+  uint32_t slab_it;                            // slabs processed so far by this CTA (buffer = slab_it & 1)
+  int quarter, half, lane;
+  bool store_thread;                           // the one thread that issues TMA stores / aux loads
+};
+
+__device__ __forceinline__ uint32_t slab_off(int row, int chunk) {          // 128B-swizzled [128 x 64] bf16 slab
+  return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// fp32 output of one thread's 32 accumulator columns (weight gradient: plain store or split-K atomics)
+__device__ __forceinline__ void epilogue_f32(const TcParams& P, int64_t m, int64_t n0, const uint32_t (&r)[32]) {
+  float* dp = P.Df + m * P.lddf + n0;
+  const int ncols = (int)min((int64_t)32, P.Ng - n0);
+  if (P.f32_mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
+  }
+}
+
+// Epilogue of one accumulator tile [128 rows x BN columns] held in TMEM at `taddr_tile` (lane bits not yet added).
+// Called by all 8 epilogue warps. (m0, n_tile0) = global coordinates of the tile's first row / column.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorMap* tmD, const CUtensorMap* tmX, EpiCtx& E,
+                                              uint32_t taddr_tile, int m0, int64_t n_tile0, bool has_work) {
+  const uint32_t taddr = taddr_tile + ((uint32_t)(E.quarter * 32) << 16);
+  const int row = E.quarter * 32 + E.lane;                      // row inside the CTA tile == TMEM lane
+  if (P.f32_mode != 0) {
+    const int64_t m = (int64_t)m0 + row;
+#pragma unroll 1
+    for (int c = E.half; c < BN / 32; c += 2) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + c * 32, r);
+      tmem_ld_wait();
+      const int64_t n0 = n_tile0 + c * 32;
+      if (m < P.Mg && n0 < P.Ng && has_work) epilogue_f32(P, m, n0, r);
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int s = 0; s < BN / 64; ++s) {
+    const int64_t n_slab = n_tile0 + s * 64;
+    if (n_slab >= P.Ng) break;                                  // uniform across the CTA
+    const uint32_t buf = E.slab_it & 1;
+    uint8_t* sD = E.stage + buf * (2 * TC_SLAB_BYTES);
+    uint8_t* sX = sD + TC_SLAB_BYTES;
+    if (E.store_thread) {
+      tma_store_wait_read<1>();                                 // the stores that read this buffer (2 slabs ago) are done
+      if (P.epi == FCMF_EPI_DGELU) {
+        mbar_expect_tx(&E.xbar[buf], TC_SLAB_BYTES);
+        tma_load_2d(sX, tmX, &E.xbar[buf], (int)n_slab, m0);
+      }
+    }
+    epi_bar_sync();                                             // (A) staging buffer is free
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + s * 64 + E.half * 32, r);
+    tmem_ld_wait();
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    const int ncols = (int)min((int64_t)32, P.Ng - n0);       // multiple of 8 (checked on the host)
+    const int64_t n0 = n_slab + E.half * 32;
     if (P.bias) {
+      if (n0 + 32 <= P.Ng) {                                    // whole chunk in range: 8 x 16-byte loads (n0 % 32 == 0)
+        const float4* b4 = reinterpret_cast<const float4*>(P.bias + n0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(P.bias + n0 + j);
+        for (int q = 0; q < 8; ++q) {
+          const float4 t = __ldg(b4 + q);
+          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n0 + j < P.Ng) v[j] += __ldg(P.bias + n0 + j);
+      }
     }
     if (P.epi == FCMF_EPI_GELU) {
-      if (P.aux) {
-        bf16* ap = P.aux + m * P.ldaux + n0;
+      if (P.has_aux) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+        for (int g = 0; g < 4; ++g) {
           uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
           for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-          *reinterpret_cast<uint4*>(ap + g * 8) = w;
+          *reinterpret_cast<uint4*>(sX + slab_off(row, E.half * 4 + g)) = w;
         }
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
     } else if (P.epi == FCMF_EPI_TANH) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = tanh_approx(v[j]);
     } else if (P.epi == FCMF_EPI_DGELU) {
-      const bf16* ap = P.aux + m * P.ldaux + n0;
+      mbar_wait(&E.xbar[buf], (E.slab_it >> 1) & 1);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
-        const uint4 w = *reinterpret_cast<const uint4*>(ap + g * 8);
+      for (int g = 0; g < 4; ++g) {
+        const uint4 w = *reinterpret_cast<const uint4*>(sX + slab_off(row, E.half * 4 + g));
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -189,47 +273,49 @@ __device__ __forceinline__ void epilogue_store(const TcParams& P, int64_t m, int
         }
       }
     }
-    bf16* dp = P.D + m * P.ldd + n0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) if (g * 8 < ncols) {
+    for (int g = 0; g < 4; ++g) {
       uint4 w; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
       for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-      *reinterpret_cast<uint4*>(dp + g * 8) = w;
+      *reinterpret_cast<uint4*>(sD + slab_off(row, E.half * 4 + g)) = w;
     }
-  } else {
-    float* dp = P.Df + m * P.lddf + n0;
-    const int ncols = (int)min((int64_t)32, P.Ng - n0);
-    if (P.f32_mode == 1) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
+    fence_proxy_async();                                        // generic-proxy writes -> visible to the TMA store
+    epi_bar_sync();                                             // (B) slab complete
+    if (E.store_thread) {
+      tma_store_2d(tmD, sD, (int)n_slab, m0);                   // clipped at the M / N edges by the tensor map
+      if (P.epi == FCMF_EPI_GELU && P.has_aux) tma_store_2d(tmX, sX, (int)n_slab, m0);
+      tma_store_commit();
     }
+    ++E.slab_it;
   }
 }
 
+// ------------------------------------------------------------------------------------------- single-CTA kernel
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tfull_bar = empty_bar + Cfg::kStages;          // [2]
+  uint8_t* stage_epi = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;                     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* x_bar = tempty_bar + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (P.f32_mode == 0) { tma_prefetch_desc(&tmD); if (P.has_aux) tma_prefetch_desc(&tmX); }
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); mbar_init(&x_bar[b], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -311,32 +397,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================================== epilogue (4 warps, one lane quarter each)
-    const int quarter = warp & 3, half = (warp - TC_EPI_WARP0) >> 2;
+    // ===================================================================== epilogue (8 warps)
+    EpiCtx E;
+    E.stage = stage_epi; E.xbar = x_bar; E.slab_it = 0;
+    E.quarter = warp & 3; E.half = (warp - TC_EPI_WARP0) >> 2; E.lane = lane;
+    E.store_thread = (warp == TC_EPI_WARP0 && lane == 0);
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < units; u += gridDim.x, ++it) {
       const int split = (int)(u % P.splits);
       const int64_t tile = u / P.splits;
       const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
-      const int kb0 = split * kb_per_split;
-      const bool has_work = kb0 < P.k_blocks;              // an empty split contributes nothing
+      const bool has_work = split * kb_per_split < P.k_blocks;   // an empty split contributes nothing
       const uint32_t buf = it & 1, use = it >> 1;
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
-      const int64_t m = (int64_t)m_blk * TC_BM + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
-        if (m < P.Mg && n0 < P.Ng && has_work) epilogue_store(P, m, n0, r);
-      }
+      epilogue_tile<BN>(P, &tmD, &tmX, E, tmem_base + buf * BN, m_blk * TC_BM, (int64_t)n_blk * BN, has_work);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
+    if (E.store_thread) tma_store_wait_all();               // shared memory must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -348,13 +428,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // A CTA pair (cluster of 2 on one TPC) owns a 256 x 256 output tile: each CTA stages its own 128 rows of A and its
 // own 128-row half of B (32 KB per stage instead of 48 KB for the same MMA work), the leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes 128 accumulator lanes into each
-// CTA's TMEM. This halves the L2 -> SM operand traffic per FLOP, which is what bounds the 1-CTA kernel.
+// CTA's TMEM; each CTA runs the epilogue of its own 128 rows.
 constexpr int TC2_BN = 256;
 constexpr int TC2_STAGE_A = TC_BM * TC_BK * 2;        // 16 KB: this CTA's 128 rows of A
 constexpr int TC2_STAGE_B = 128 * TC_BK * 2;          // 16 KB: this CTA's half of the 256 B rows
 constexpr int TC2_STAGE = TC2_STAGE_A + TC2_STAGE_B;
-constexpr int TC2_STAGES = 6;
-constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE + 1024 + 256;
+constexpr int TC2_STAGES = 4;
+constexpr int TC2_SMEM = TC2_STAGES * TC2_STAGE + TC_EPI_SMEM + 1024 + TC_CTRL_BYTES;
 constexpr uint32_t TC2_PEER_MASK = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even (leader) CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -402,15 +482,18 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  
 
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC2_STAGES * TC2_STAGE);
-  uint64_t* empty_bar = full_bar + TC2_STAGES;
-  uint64_t* tfull_bar = empty_bar + TC2_STAGES;           // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;                   // [2], only the leader copy is used (16 arrivals: 8 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* stage_epi = smem + TC2_STAGES * TC2_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tfull_bar = empty_bar + 8;                    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                   // [2], only the leader copy is used (16 arrivals: 8 warps x 2 CTAs)
+  uint64_t* x_bar = tempty_bar + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -419,8 +502,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (P.f32_mode == 0) { tma_prefetch_desc(&tmD); if (P.has_aux) tma_prefetch_desc(&tmX); }
     for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); mbar_init(&x_bar[b], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
@@ -499,31 +583,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    const int quarter = warp & 3, half = (warp - TC_EPI_WARP0) >> 2;
+    EpiCtx E;
+    E.stage = stage_epi; E.xbar = x_bar; E.slab_it = 0;
+    E.quarter = warp & 3; E.half = (warp - TC_EPI_WARP0) >> 2; E.lane = lane;
+    E.store_thread = (warp == TC_EPI_WARP0 && lane == 0);
     uint32_t it = 0;
     for (int64_t u = cluster_id; u < units; u += n_clusters, ++it) {
       const int split = (int)(u % P.splits);
       const int64_t tile = u / P.splits;
       const int n_blk = (int)(tile % P.n_tiles), m_blk = (int)(tile / P.n_tiles);
-      const int kb0 = split * kb_per_split;
-      const bool has_work = kb0 < P.k_blocks;
+      const bool has_work = split * kb_per_split < P.k_blocks;
       const uint32_t buf = it & 1, use = it >> 1;
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
-      const int64_t m = (int64_t)m_blk * 256 + (int64_t)rank * 128 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * TC2_BN;
-#pragma unroll 1
-      for (int c = half; c < TC2_BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int64_t n0 = (int64_t)n_blk * TC2_BN + c * 32;
-        if (m < P.Mg && n0 < P.Ng && has_work) epilogue_store(P, m, n0, r);
-      }
+      epilogue_tile<TC2_BN>(P, &tmD, &tmX, E, tmem_base + buf * TC2_BN, m_blk * 256 + (int)rank * 128,
+                            (int64_t)n_blk * TC2_BN, has_work);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cta(&tempty_bar[buf], 0);
     }
+    if (E.store_thread) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -584,8 +663,10 @@ bool gemm_tc_supported_wgrad(int64_t M, int64_t N, int64_t K, int64_t lddy, int6
   return ok16(dY) && ok16(X);
 }
 
+struct Maps { CUtensorMap a, b, d, x; };
+
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, cudaStream_t st) {
+static int launch(const Maps& m, const TcParams& P, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set[64] = {false};                       // per instantiation, per device
@@ -597,7 +678,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& 
   }
   const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;
   const int grid = (int)(units < sm_count() ? units : sm_count());
-  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, P);
+  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(m.a, m.b, m.d, m.x, P);
   FCMF_LAUNCH_OK();
   return 0;
 }
@@ -610,7 +691,7 @@ static bool use_2cta() {
 }
 
 template <bool A_MN, bool B_MN>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& P, cudaStream_t st) {
+static int launch2(const Maps& m, const TcParams& P, cudaStream_t st) {
   auto kern = gemm_tc2_kernel<A_MN, B_MN>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -622,7 +703,7 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams&
   const int64_t units = (int64_t)P.m_tiles * P.n_tiles * P.splits;
   const int64_t pairs = sm_count() / 2;
   const int grid = 2 * (int)(units < pairs ? units : pairs);
-  kern<<<grid, TC_THREADS, TC2_SMEM, st>>>(ta, tb, P);
+  kern<<<grid, TC_THREADS, TC2_SMEM, st>>>(m.a, m.b, m.d, m.x, P);
   FCMF_LAUNCH_OK();
   return 0;
 }
@@ -631,31 +712,42 @@ int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const flo
                void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K, int epi, cudaStream_t st) {
   TcParams P{};
   P.Mg = M; P.Ng = N; P.Kg = K;
-  P.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   P.k_blocks = (int)((K + TC_BK - 1) / TC_BK);
   P.splits = 1;
-  P.bias = bias; P.D = (bf16*)D; P.ldd = ldd; P.aux = (bf16*)aux; P.ldaux = ldaux; P.epi = epi; P.f32_mode = 0;
+  P.bias = bias; P.epi = epi; P.f32_mode = 0;
+  P.has_aux = (aux != nullptr && (epi == FCMF_EPI_GELU || epi == FCMF_EPI_DGELU)) ? 1 : 0;
+  Maps m;
+  if (int r = make_map(&m.d, D, M, N, ldd, 64, TC_BM)) return r;                    // output slabs: box [64 cols][128 rows]
+  if (P.has_aux) { if (int r = make_map(&m.x, aux, M, N, ldaux, 64, TC_BM)) return r; }
+  else m.x = m.d;
   if (use_2cta() && N % 256 == 0 && ((M + 255) / 256) * (N / 256) >= sm_count() / 2) {
     P.m_tiles = (int)((M + 255) / 256);
     P.n_tiles = (int)(N / 256);
-    CUtensorMap ta2, tb2;
-    if (int r = make_map(&ta2, A, M, K, lda, TC_BK, 128)) return r;
-    if (int r = make_map(&tb2, B, N, K, ldb, TC_BK, 128)) return r;
-    return launch2<false, false>(ta2, tb2, P, st);
+    if (int r = make_map(&m.a, A, M, K, lda, TC_BK, 128)) return r;
+    if (int r = make_map(&m.b, B, N, K, ldb, TC_BK, 128)) return r;
+    return launch2<false, false>(m, P, st);
   }
+  P.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
   // 256-wide tiles unless that leaves SMs idle
   const int64_t tiles256 = (int64_t)P.m_tiles * ((N + 255) / 256);
   const bool wide = (N % 256 == 0 || N > 1024) && tiles256 >= sm_count();
-  CUtensorMap ta, tb;
-  if (int r = make_map(&ta, A, M, K, lda, TC_BK, TC_BM)) return r;
+  if (int r = make_map(&m.a, A, M, K, lda, TC_BK, TC_BM)) return r;
   if (wide) {
     P.n_tiles = (int)((N + 255) / 256);
-    if (int r = make_map(&tb, B, N, K, ldb, TC_BK, 256)) return r;
-    return launch<256, false, false>(ta, tb, P, st);
+    if (int r = make_map(&m.b, B, N, K, ldb, TC_BK, 256)) return r;
+    return launch<256, false, false>(m, P, st);
   }
   P.n_tiles = (int)((N + 127) / 128);
-  if (int r = make_map(&tb, B, N, K, ldb, TC_BK, 128)) return r;
-  return launch<128, false, false>(ta, tb, P, st);
+  if (int r = make_map(&m.b, B, N, K, ldb, TC_BK, 128)) return r;
+  return launch<128, false, false>(m, P, st);
+}
+
+static int pick_splits(int64_t tiles, int64_t workers, int k_blocks) {
+  int splits = (int)((workers + tiles - 1) / tiles);
+  if (splits > k_blocks) splits = k_blocks;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && (int64_t)(splits - 1) * ((k_blocks + splits - 1) / splits) >= k_blocks) --splits;   // no empty split
+  return splits;
 }
 
 int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N, int64_t K,
@@ -663,42 +755,28 @@ int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, floa
   // dW[N,K] = sum_m dY[m,n] X[m,k]: GEMM rows = N (out features), cols = K (in features), reduction = M rows.
   TcParams P{};
   P.Mg = N; P.Ng = K; P.Kg = M;
-  P.m_tiles = (int)((N + TC_BM - 1) / TC_BM);
   P.k_blocks = (int)((M + TC_BK - 1) / TC_BK);
-  if (use_2cta() && N % 256 == 0 && K % 256 == 0) {
+  P.Df = dW; P.lddf = K; P.epi = FCMF_EPI_NONE;
+  Maps m;
+  if (int r = make_map(&m.a, dY, M, N, lddy, 64, TC_BK)) return r;       // box [64 features][64 rows]
+  if (int r = make_map(&m.b, X, M, K, ldx, 64, TC_BK)) return r;
+  m.d = m.a; m.x = m.a;                                                  // unused in fp32 mode
+  const bool two = use_2cta() && N % 256 == 0 && K % 256 == 0;
+  int bn = 256;
+  if (two) {
     P.m_tiles = (int)(N / 256);
     P.n_tiles = (int)(K / 256);
-    const int64_t tiles2 = (int64_t)P.m_tiles * P.n_tiles, pairs = sm_count() / 2;
-    int splits = (int)((pairs + tiles2 - 1) / tiles2);
-    if (splits > P.k_blocks) splits = P.k_blocks;
-    if (splits < 1) splits = 1;
-    while (splits > 1 && (int64_t)(splits - 1) * ((P.k_blocks + splits - 1) / splits) >= P.k_blocks) --splits;
-    P.splits = splits;
-    P.Df = dW; P.lddf = K; P.epi = FCMF_EPI_NONE;
-    P.f32_mode = (splits == 1 && !accumulate) ? 1 : 2;
-    if (P.f32_mode == 2 && !accumulate) FCMF_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st));
-    CUtensorMap ta2, tb2;
-    if (int r = make_map(&ta2, dY, M, N, lddy, 64, TC_BK)) return r;
-    if (int r = make_map(&tb2, X, M, K, ldx, 64, TC_BK)) return r;
-    return launch2<true, true>(ta2, tb2, P, st);
+    P.splits = pick_splits((int64_t)P.m_tiles * P.n_tiles, sm_count() / 2, P.k_blocks);
+  } else {
+    bn = (K % 256 == 0) ? 256 : 128;
+    P.m_tiles = (int)((N + TC_BM - 1) / TC_BM);
+    P.n_tiles = (int)((K + bn - 1) / bn);
+    P.splits = pick_splits((int64_t)P.m_tiles * P.n_tiles, sm_count(), P.k_blocks);
   }
-  const bool wide = (K % 256 == 0);
-  const int bn = wide ? 256 : 128;
-  P.n_tiles = (int)((K + bn - 1) / bn);
-  const int64_t tiles = (int64_t)P.m_tiles * P.n_tiles;
-  int splits = (int)((sm_count() + tiles - 1) / tiles);
-  if (splits > P.k_blocks) splits = P.k_blocks;
-  if (splits < 1) splits = 1;
-  // make every split non-empty
-  while (splits > 1 && (int64_t)(splits - 1) * ((P.k_blocks + splits - 1) / splits) >= P.k_blocks) --splits;
-  P.splits = splits;
-  P.Df = dW; P.lddf = K; P.epi = FCMF_EPI_NONE;
-  P.f32_mode = (splits == 1 && !accumulate) ? 1 : 2;
+  P.f32_mode = (P.splits == 1 && !accumulate) ? 1 : 2;
   if (P.f32_mode == 2 && !accumulate) FCMF_CUDA_OK(cudaMemsetAsync(dW, 0, sizeof(float) * N * K, st));
-  CUtensorMap ta, tb;
-  if (int r = make_map(&ta, dY, M, N, lddy, 64, TC_BK)) return r;       // box [64 features][64 rows]
-  if (int r = make_map(&tb, X, M, K, ldx, 64, TC_BK)) return r;
-  return wide ? launch<256, true, true>(ta, tb, P, st) : launch<128, true, true>(ta, tb, P, st);
+  if (two) return launch2<true, true>(m, P, st);
+  return bn == 256 ? launch<256, true, true>(m, P, st) : launch<128, true, true>(m, P, st);
 }
 
 }  // namespace fcmf

@@ -245,6 +245,7 @@ extern "C" int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, 
     const bool ok = dtype == FCMF_BF16 && attn_tc_supported(a, ldctx, ctx);
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_fwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
     if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_fwd(a, ctx, ldctx, lse, as_stream(stream));
+    if (eng != FCMF_ENGINE_SIMT && attn_q1_supported(a)) return attn_q1_fwd(a, ctx, ldctx, lse, dtype, as_stream(stream));
   }
   const size_t smem = sizeof(float) * ((size_t)2 * a.Lk * (a.dh + 1) + (size_t)AT_WARPS * (a.dh + a.Lk));
   const unsigned grid = (unsigned)(a.NP * a.heads);
@@ -274,6 +275,7 @@ extern "C" int fcmf_attn_bwd(const fcmf_attn_desc* d, const void* ctx, int64_t l
     const bool ok = dtype == FCMF_BF16 && dbias == nullptr && attn_tc_supported(a, ldctx, ctx) && (lddctx % 8) == 0;
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_bwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
     if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_bwd(a, ctx, ldctx, dctx, lddctx, lse, delta, dq, dk, dv, st);
+    if (eng != FCMF_ENGINE_SIMT && dbias == nullptr && attn_q1_supported(a)) return attn_q1_bwd(a, ctx, ldctx, dctx, lddctx, lse, dq, dk, dv, dtype, st);
   }
   const size_t smem_q = sizeof(float) * ((size_t)2 * a.Lk * (a.dh + 1) + (size_t)AT_WARPS * (2 * a.dh + a.Lk));
   const size_t smem_kv = sizeof(float) * ((size_t)2 * a.Lq * (a.dh + 1) + 2 * (size_t)a.Lq + (size_t)AT_WARPS * (2 * a.dh + 2 * a.Lq));

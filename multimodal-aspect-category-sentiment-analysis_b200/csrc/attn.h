@@ -29,4 +29,10 @@ int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
                 float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
 int attn_engine();      // 0 auto, 1 CUDA-core, 2 tcgen05 (fcmf_set_attn_engine)
 
+// single-query kernels (attn_q1.cu): Lq == 1, no per-pair bias, either dtype
+bool attn_q1_supported(const AttnDev& a);
+int attn_q1_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, int dtype, cudaStream_t st);
+int attn_q1_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
+                void* dq, void* dk, void* dv, int dtype, cudaStream_t st);
+
 }  // namespace fcmf

@@ -310,7 +310,19 @@ def main():
     if not args.no_second_mode:
         orows = "live" if args.rows == "full" else "full"
         ms_o, l_o = timed(lambda: step(res, orows), max(3, min(args.steps, 10)), 3)
-        other = {"rows": orows, "value": n_gpus * B / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o, "gpu_launches": l_o}
+        other = {"rows": orows, "value": n_gpus * B / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o, "gpu_launches": l_o,
+                 "cuda_graph": False}
+        if orows == "live":
+            # live rows: the step's GPU work is shorter than Python's launch path -> also replay it as ONE CUDA graph
+            # (same kernels, same inputs; reported beside the eager number, never instead of it)
+            try:
+                graphed = importlib.import_module(PKG + ".graphed")
+                gstep = graphed.GraphedFusionStep(model, res, aspects=A, rows="live", reducer=reducer)
+                ms_g, _ = timed(lambda: gstep(), max(3, min(args.steps, 10)) * 4, 3)
+                other["graph_replay"] = {"value": n_gpus * B / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                                         "launches_per_replay": int(l_o)}
+            except Exception as e:                                   # capture is an optimisation, never a requirement
+                other["graph_replay"] = {"unavailable": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:

@@ -39,11 +39,18 @@ class Attention(nn.Module):
         self.attention_weights = None
 
     def _project(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-        """x [B,T,E] times per-head [nh,E,dh] as ONE GEMM against the [nh*dh, E] stacking -> [B, nh, T, dh]."""
+        """x [B,T,E] times per-head [nh,E,dh] as ONE GEMM against the [nh*dh, E] stacking -> [B, slots, T, dh].
+
+        The reference pairs input ``k.repeat(nh,1,1)[n]`` (batch n % B) with weight ``w.repeat(B,1,1)[n]`` (head n % nh)
+        and then places entry n = c*B + b in output slot c of batch b (mm_modeling.py:79-85, 130): slot c of batch b uses
+        head (c*B + b) % nh. The GEMM computes every head for every row; the slot->head map is a gather on the head axis."""
         B, T, E = x.shape
-        w2 = w.permute(0, 2, 1).reshape(self.n_head * self.hidden_dim, E)
-        y = Fn.linear(x.reshape(B * T, E), w2, None)
-        return y.view(B, T, self.n_head, self.hidden_dim).permute(0, 2, 1, 3)
+        nh, dh = self.n_head, self.hidden_dim
+        w2 = w.permute(0, 2, 1).reshape(nh * dh, E)
+        y = Fn.linear(x.reshape(B * T, E), w2, None).view(B, T, nh, dh)
+        slot_head = (torch.arange(nh, device=x.device).view(1, nh) * B + torch.arange(B, device=x.device).view(B, 1)) % nh
+        y = torch.gather(y, 2, slot_head.view(B, 1, nh, 1).expand(B, T, nh, dh))                 # [B, T, slot, dh]
+        return y.permute(0, 2, 1, 3)
 
     def forward(self, k, q, memory_len=None):
         if k.dim() == 2:

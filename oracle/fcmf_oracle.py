@@ -206,8 +206,14 @@ def head_attention(k_in: Tensor, q_in: Tensor, w_kx: Tensor, w_qx: Tensor, proj_
     tril(q_len x k_len) mask on self- AND cross-attention (lines 115-118), a 1-D one a length mask;
     masked_fill(-1e4) (line 124); heads are concatenated on the feature axis (line 130)."""
     nh = w_kx.shape[0]
-    kx = torch.einsum("bke,hed->hbkd", k_in, w_kx)
-    qx = torch.einsum("bqe,hed->hbqd", q_in, w_qx)
+    # Entry n of the reference's flattened batch pairs INPUT  k.repeat(nh,1,1)[n]      = batch  n % B   (head-major)
+    #                                             with WEIGHT w_kx.repeat(B,1,1)[n]   = head   n % nh  (batch-major)
+    # (mm_modeling.py:79-85), and torch.split/cat (line 130) puts entry n = c*B + b into output slot c of batch b.
+    # So slot c of batch b is projected with head weights (c*B + b) % nh -- a quirk that is part of the contract.
+    B = k_in.shape[0]
+    slot_head = (torch.arange(nh).view(nh, 1) * B + torch.arange(B).view(1, B)) % nh          # [slot c, batch b]
+    kx = torch.einsum("bke,cbed->cbkd", k_in, w_kx[slot_head])
+    qx = torch.einsum("bqe,cbed->cbqd", q_in, w_qx[slot_head])
     score = torch.matmul(qx, kx.transpose(-1, -2)) / math.sqrt(w_kx.shape[-1])
     q_len, k_len = score.shape[-2], score.shape[-1]
     if causal:

@@ -8,76 +8,92 @@ namespace fcmf {
 constexpr int LN_WARPS = 4;
 
 // ------------------------------------------------------------------------------------------- LayerNorm fwd
+// Persistent warps (grid-stride over rows): gamma/beta are staged ONCE per block in shared memory -- the first version
+// re-read them per row with 2*H/32 scalar loads per lane and was LSU-issue bound (ncu: 533 warp-instructions per row,
+// 24 % of DRAM peak) -- and the next row's 16-byte loads are issued before the current row's reductions.
 template <typename T, int VPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t* __restrict__ res_idx,
               const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
               float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H, float eps) {
   constexpr int N = Vec16<T>::N;
+  extern __shared__ float ln_params[];                          // gamma[H] | beta[H]: 16-byte conflict-free reads per row
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const T* xr = x + row * H;
-  const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
-  float v[VPL][N];
-  float sum = 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) { ln_params[c] = gamma[c]; ln_params[H + c] = beta[c]; }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < M; row += stride) {
+    const T* xr = x + row * H;
+    const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
+    float v[VPL][N];
+    float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * N;
-    if (c < H) {
-      Vec16<T> a; a.load(xr + c);
-      if (rr) { Vec16<T> b; b.load(rr + c);
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * N;
+      if (c < H) {
+        Vec16<T> a; a.load(xr + c);
+        if (rr) { Vec16<T> b; b.load(rr + c);
 #pragma unroll
-        for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
+          for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
 #pragma unroll
-      for (int j = 0; j < N; ++j) { v[i][j] = a.v[j]; sum += a.v[j]; }
-    } else {
+        for (int j = 0; j < N; ++j) { v[i][j] = a.v[j]; sum += a.v[j]; }
+      } else {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[i][j] = 0.f;
+        for (int j = 0; j < N; ++j) v[i][j] = 0.f;
+      }
     }
-  }
-  const float mu = warp_sum(sum) / (float)H;
-  float sq = 0.f;
+    const float mu = warp_sum(sum) / (float)H;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * N;
-    if (c < H) {
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * N;
+      if (c < H) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) { const float d = v[i][j] - mu; sq += d * d; }
+        for (int j = 0; j < N; ++j) { const float d = v[i][j] - mu; sq += d * d; }
+      }
     }
-  }
-  const float var = warp_sum(sq) / (float)H;          // biased variance, mm_modeling.py:169
-  const float rs = 1.0f / sqrtf(var + eps);           // eps inside the sqrt, mm_modeling.py:170
-  if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
-  T* yr = y + row * H;
+    const float var = warp_sum(sq) / (float)H;          // biased variance, mm_modeling.py:169
+    const float rs = 1.0f / sqrtf(var + eps);           // eps inside the sqrt, mm_modeling.py:170
+    if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+    T* yr = y + row * H;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * N;
-    if (c < H) {
-      Vec16<T> o;
+    for (int i = 0; i < VPL; ++i) {
+      const int c = (i * 32 + lane) * N;
+      if (c < H) {
+        Vec16<T> o;
 #pragma unroll
-      for (int j = 0; j < N; ++j) o.v[j] = gamma[c + j] * ((v[i][j] - mu) * rs) + beta[c + j];
-      o.store(yr + c);
+        for (int j = 0; j < N; j += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(ln_params + c + j);
+          const float4 bv = *reinterpret_cast<const float4*>(ln_params + H + c + j);
+          o.v[j] = fmaf(gv.x, (v[i][j] - mu) * rs, bv.x);
+          o.v[j + 1] = fmaf(gv.y, (v[i][j + 1] - mu) * rs, bv.y);
+          o.v[j + 2] = fmaf(gv.z, (v[i][j + 2] - mu) * rs, bv.z);
+          o.v[j + 3] = fmaf(gv.w, (v[i][j + 3] - mu) * rs, bv.w);
+        }
+        o.store(yr + c);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------- LayerNorm bwd
 template <typename T, int VPL>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* __restrict__ x, const T* __restrict__ res,
               const int32_t* __restrict__ res_idx, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H) {
   constexpr int N = Vec16<T>::N;
-  extern __shared__ float red[];                      // [LN_WARPS][2][H]
+  extern __shared__ float red[];                      // [LN_WARPS][2][H] column partial sums | gamma[H]
+  float* gsm = red + (size_t)LN_WARPS * 2 * H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float g[VPL][N], dg[VPL][N], db[VPL][N];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) gsm[c] = gamma[c];
+  __syncthreads();
+  float dg[VPL][N], db[VPL][N];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int c = (i * 32 + lane) * N;
 #pragma unroll
-    for (int j = 0; j < N; ++j) { g[i][j] = (c < H) ? gamma[c + j] : 0.f; dg[i][j] = 0.f; db[i][j] = 0.f; }
+    for (int j = 0; j < N; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; }
   }
   const int64_t stride = (int64_t)gridDim.x * LN_WARPS;
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += stride) {
@@ -98,10 +114,16 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
         if (rr) { Vec16<T> b; b.load(rr + c);
 #pragma unroll
           for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
+        float gq[N];
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+          const float4 gv = *reinterpret_cast<const float4*>(gsm + c + j);
+          gq[j] = gv.x; gq[j + 1] = gv.y; gq[j + 2] = gv.z; gq[j + 3] = gv.w;
+        }
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           xh[i][j] = (a.v[j] - mu) * rs;
-          gy[i][j] = d.v[j] * g[i][j];
+          gy[i][j] = d.v[j] * gq[j];
           s1 += gy[i][j];
           s2 += gy[i][j] * xh[i][j];
           dg[i][j] += d.v[j] * xh[i][j];
@@ -148,8 +170,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
 template <typename T, int VPL>
 static int ln_fwd_launch(const void* x, const void* res, const int32_t* idx, const float* gamma, const float* beta,
                          void* y, float* mean, float* rstd, int64_t M, int H, float eps, cudaStream_t st) {
-  const unsigned grid = (unsigned)((M + LN_WARPS - 1) / LN_WARPS);
-  ln_fwd_kernel<T, VPL><<<grid, LN_WARPS * 32, 0, st>>>((const T*)x, (const T*)res, idx, gamma, beta, (T*)y, mean,
+  int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
+  const int64_t cap = (int64_t)sm_count() * 16;                 // up to 64 warps per SM, each looping over rows
+  if (blocks > cap) blocks = cap;
+  const unsigned grid = (unsigned)blocks;
+  ln_fwd_kernel<T, VPL><<<grid, LN_WARPS * 32, sizeof(float) * 2 * H, st>>>((const T*)x, (const T*)res, idx, gamma, beta, (T*)y, mean,
                                                          rstd, M, H, eps);
   FCMF_LAUNCH_OK();
   return 0;
@@ -162,7 +187,7 @@ static int ln_bwd_launch(const void* dy, const void* dy_add, const void* x, cons
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  const size_t smem = sizeof(float) * LN_WARPS * 2 * H;
+  const size_t smem = sizeof(float) * (LN_WARPS * 2 + 1) * H;
   ln_bwd_kernel<T, VPL><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
       (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, dgamma, dbeta, M, H);
   FCMF_LAUNCH_OK();
@@ -275,7 +300,7 @@ extern "C" int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_id
   const int H = (int)H64;
   FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_fwd: bad shape");
   FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_fwd: H=%d must be a multiple of the 16-byte vector", H);
-  FCMF_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)), "ln_fwd: pointers must be 16-byte aligned");
+  FCMF_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)) && aligned16(gamma) && aligned16(beta), "ln_fwd: pointers must be 16-byte aligned");
   if (M == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, st);

@@ -25,6 +25,7 @@ constexpr int ATC_TILE = 128;                   // rows per CTA tile (UMMA M)
 constexpr int ATC_BLK = 64;                     // block width
 constexpr uint32_t ATC_TILE_BYTES = ATC_TILE * 128;   // 16 KB
 constexpr uint32_t ATC_BLK_BYTES = ATC_BLK * 128;     // 8 KB
+constexpr float kLog2e = 1.44269504088896340736f;
 
 // ------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,20 +116,28 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // rows [row0, row0+tile_rows) of a segmented [L x 64] bf16 matrix of (problem p, head h) -> swizzled tile; rows >= L are 0
 __device__ __forceinline__ void stage_seg(uint8_t* tile, const SegDev (&s)[2], int p, int h, int row0, int tile_rows, int L) {
-  const bf16* safe = reinterpret_cast<const bf16*>(s[0].ptr);
-  for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
-    const int r = e >> 3, c = e & 7, gr = row0 + r;
+  // segment bases are per (problem, head): resolve the group indices once, not per 16-byte chunk
+  const int c = threadIdx.x & 7;
+  const int rows0 = s[0].rows;
+  const bf16* base0 = reinterpret_cast<const bf16*>(s[0].ptr) + ((int64_t)(s[0].idx ? s[0].idx[p] : p) * rows0) * s[0].ld + (int64_t)h * 64 + c * 8;
+  const bf16* base1 = s[1].rows ? reinterpret_cast<const bf16*>(s[1].ptr) + ((int64_t)(s[1].idx ? s[1].idx[p] : p) * s[1].rows) * s[1].ld + (int64_t)h * 64 + c * 8 : base0;
+  const int64_t ld0 = s[0].ld, ld1 = s[1].ld;
+  for (int r = threadIdx.x >> 3; r < tile_rows; r += ATC_THREADS / 8) {
+    const int gr = row0 + r;
     const bool ok = gr < L;
-    cp_async16(tile + swz(r, c), ok ? seg_row<bf16>(s, p, gr, h, 64) + c * 8 : safe, ok);
+    const bf16* src = gr < rows0 ? base0 + gr * ld0 : base1 + (gr - rows0) * ld1;
+    cp_async16(tile + swz(r, c), ok ? src : base0, ok);
   }
 }
 // same for a plain [NP*L, ld] activation (ctx / dctx)
 __device__ __forceinline__ void stage_plain(uint8_t* tile, const bf16* base, int64_t ld, int64_t prow0, int h, int row0,
                                             int tile_rows, int L) {
-  for (int e = threadIdx.x; e < tile_rows * 8; e += ATC_THREADS) {
-    const int r = e >> 3, c = e & 7, gr = row0 + r;
+  const int c = threadIdx.x & 7;
+  const bf16* b0 = base + prow0 * ld + (int64_t)h * 64 + c * 8;
+  for (int r = threadIdx.x >> 3; r < tile_rows; r += ATC_THREADS / 8) {
+    const int gr = row0 + r;
     const bool ok = gr < L;
-    cp_async16(tile + swz(r, c), ok ? base + (prow0 + gr) * ld + (int64_t)h * 64 + c * 8 : base, ok);
+    cp_async16(tile + swz(r, c), ok ? b0 + gr * ld : base, ok);
   }
 }
 // thread-owned row: write 32 consecutive bf16 (cols c0..c0+31 of a 64-col block) of row r into a swizzled tile
@@ -188,6 +197,7 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   const int ph = blockIdx.x / mtiles;
   const int p = ph / a.heads, h = ph % a.heads;
   const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE;
+  const float scale2 = a.scale * kLog2e;                        // scores are handled in the log2 domain: one FFMA + one MUFU.EX2 each
 
   if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
   if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
@@ -196,7 +206,7 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
   cp_async_commit();
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
+  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
   cp_async_wait_all();
   a_fence_async();
   a_tc_before();
@@ -220,7 +230,11 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
     uint32_t r[32];
     a_tmem_ld32(tS + lane_addr + c * 32, r);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * a.scale + msk[c * 32 + j]);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
+      mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale2, m4.x), fmaf(__uint_as_float(r[j + 1]), scale2, m4.y)),
+                           fmaxf(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z), fmaf(__uint_as_float(r[j + 3]), scale2, m4.w))));
+    }
   }
   red[grp * 128 + trow] = mx;
   __syncthreads();
@@ -232,9 +246,13 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
     float v[32];
     a_tmem_ld32(tS + lane_addr + c * 32, r);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = __expf(__uint_as_float(r[j]) * a.scale + msk[c * 32 + j] - mx);
-      sum += v[j];
+    for (int j = 0; j < 32; j += 4) {
+      const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
+      v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, m4.x) - mx);
+      v[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, m4.y) - mx);
+      v[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z) - mx);
+      v[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, m4.w) - mx);
+      sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
     }
     store_row32(Pblk(c >> 1), trow, (c & 1) * 32, v);
   }
@@ -261,7 +279,7 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
     a_tmem_ld32(tO + lane_addr + grp * 32, r);
     if (row < Lq) store_out32(ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32, r, 1.0f / sum);
   }
-  if (grp == 0 && row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = mx + __logf(sum);
+  if (grp == 0 && row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = (mx + __log2f(sum)) * 0.69314718055994530942f;   // back to natural log
   a_tc_before();
   __syncthreads();
   if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
@@ -291,6 +309,7 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   const int ph = blockIdx.x / mtiles;
   const int p = ph / a.heads, h = ph % a.heads;
   const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE, HD = a.heads * 64;
+  const float scale2 = a.scale * kLog2e;
 
   if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
   if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
@@ -300,7 +319,7 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
   cp_async_commit();
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] : 0.f) : -INFINITY;
+  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
 
   // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each
   const int row = row0 + trow;
@@ -326,7 +345,7 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   a_tc_before();
   __syncthreads();
   a_tc_after();
-  float dl = 0.f, l = 0.f;
+  float dl = 0.f, l = 0.f, l2 = 0.f;
   {
     const float* scratch = reinterpret_cast<const float*>(Ds);
     dl = scratch[trow] + scratch[128 + trow];
@@ -334,6 +353,7 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
       l = lse[stat];
       if (grp == 0) delta[stat] = dl;
     }
+    l2 = l * kLog2e;
   }
   __syncthreads();                                               // scratch (aliases dS) fully read before it is rewritten
   const uint32_t tm = sh->tmem;
@@ -357,9 +377,14 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
       a_tmem_ld32(tS + lane_addr + grp * 32, rs);
       a_tmem_ld32(tP + lane_addr + grp * 32, rp);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pj = __expf(__uint_as_float(rs[j]) * a.scale + msk[b * 64 + grp * 32 + j] - l);
-        v[j] = (row < Lq) ? pj * (__uint_as_float(rp[j]) - dl) : 0.f;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 m4 = *reinterpret_cast<const float4*>(msk + b * 64 + grp * 32 + j);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float pj = ex2_approx(fmaf(__uint_as_float(rs[j + u]), scale2, mm[u]) - l2);
+          v[j + u] = (row < Lq) ? pj * (__uint_as_float(rp[j + u]) - dl) : 0.f;
+        }
       }
       store_row32(Ds, trow, grp * 32, v);
     }
@@ -422,12 +447,13 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
   cp_async_commit();
   const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
   for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
-    ls[i] = i < Lq ? lse[stat0 + i] : INFINITY;          // exp(s - inf) = 0 for the padded queries
+    ls[i] = i < Lq ? lse[stat0 + i] * kLog2e : INFINITY;  // log2 domain; exp2(s - inf) = 0 for the padded queries
     dls[i] = i < Lq ? delta[stat0 + i] : 0.f;
   }
   const int key = key0 + trow;
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  const float mk = (key < Lk && madd) ? madd[key] : 0.f;
+  const float mk = (key < Lk && madd) ? madd[key] * kLog2e : 0.f;
+  const float scale2 = a.scale * kLog2e;
   cp_async_wait_all();
   a_fence_async();
   a_tc_before();
@@ -463,7 +489,7 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int qi = b * 64 + grp * 32 + j;
-        const float pj = (key < Lk) ? __expf(__uint_as_float(rs[j]) * a.scale + mk - ls[qi]) : 0.f;
+        const float pj = (key < Lk) ? ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, mk) - ls[qi]) : 0.f;
         pv[j] = pj;
         dsv[j] = pj * (__uint_as_float(rp[j]) - dls[qi]);
       }

@@ -36,13 +36,18 @@ def parse():
     ap.add_argument("--rows", default=os.environ.get("FCMF_BENCH_ROWS", "full"), choices=["full", "live"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (samples)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--hidden", type=int, default=768, help="768 = XLM-R-base dims (configs[1]); 1024 = XLM-R-large (configs[4])")
+    ap.add_argument("--heads", type=int, default=12)
+    ap.add_argument("--inter", type=int, default=3072)
+    ap.add_argument("--seq-len", type=int, default=170)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-second-mode", action="store_true")
     return ap.parse_args()
 
 
 def workload_name(dims, rows):
-    return (f"BASELINE.json configs[1]: FCMF fine-tuning fusion fwd+bwd, per-GPU batch {dims.batch}, {dims.aspects} aspects "
+    which = "configs[1]" if dims.hidden == 768 and dims.seq_len == 170 else "configs[4]-style (XLM-R-large dims)"
+    return (f"BASELINE.json {which}: FCMF fine-tuning fusion fwd+bwd, per-GPU batch {dims.batch}, {dims.aspects} aspects "
             f"folded into one launch sequence, L={dims.seq_len}, {dims.num_imgs} images x 49 grid tokens (2048-d), "
             f"{dims.num_roi} ROIs/image, H={dims.hidden}")
 
@@ -105,7 +110,7 @@ def cpu_step_fn(dims, torch):
                                 batch["added_attention_mask"], batch["labels"], params, dims.heads, dims.num_imgs,
                                 dims.num_roi)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -139,7 +144,7 @@ def run_reference(args):
     synth = pkg.synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    base = synth.FusionDims(batch=args.batch)
+    base = synth.FusionDims(batch=args.batch, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
     d1 = synth.FusionDims(**{**base.to_dict(), "batch": 1})
     s1 = cpu_step_fn(d1, torch)
     t0 = time.perf_counter(); s1(); t1 = time.perf_counter() - t0
@@ -191,8 +196,10 @@ def main():
     n_gpus = world
 
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    dims = synth.FusionDims(batch=args.batch)
+    dims = synth.FusionDims(batch=args.batch, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
     B, A = dims.batch, dims.aspects
+    mm = importlib.import_module(PKG + ".fcmf_framework.mm_modeling")      # model dims are module constants, as in the reference
+    mm.HIDDEN_SIZE, mm.NUM_ATTENTION_HEADS, mm.INTERMEDIATE_SIZE = dims.hidden, dims.heads, dims.inter
     model = pkg.FCMF(None, num_labels=dims.num_labels, num_imgs=dims.num_imgs, num_roi=dims.num_roi)
     model.load_state_dict(synth.make_params(dims, seed=42), strict=True)
     model = model.to(dev).eval()                     # eval(): dropout off, the mode parity is defined in
@@ -280,10 +287,17 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1590.0 if not peaks else peaks.get("bf16_tflops", 1590.0)))
     achieved_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     n_gemm = len(timed_entries) // max(args.steps, 1)
+    traffic = {}
+    try:                                   # dram__bytes_read+write of the heaviest GEMM launch, from the committed ncu capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma.kind::f16, TMA-fed, TMEM accumulators)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)",
-                "traffic": None, "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / max(args.steps, 1),
+                "traffic": traffic.get("traffic"), "traffic_algorithmic": traffic.get("algorithmic_bytes"),
+                "traffic_launch": traffic.get("launch"), "traffic_source": traffic.get("source"),
+                "gemm_launches_per_step": n_gemm, "gemm_ms_per_step": g_ms / max(args.steps, 1),
                 "gemm_flops_per_step": g_flops / max(args.steps, 1), "gemm_share_of_step": (g_ms / max(args.steps, 1)) / ms if ms else None,
                 "note": "achieved = sum(2*M*N*K) over every GEMM launch of the timed steps / sum of their CUDA-event durations "
                         "(events recorded on the launching stream around each launch; includes the bias column-sum that "

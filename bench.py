@@ -234,11 +234,33 @@ def main():
             reducer.finish()
         return logits, loss
 
+    # end-to-end step: every step's inputs come from pinned host memory; the copy of step i+1's inputs is issued on a
+    # copy stream while step i computes (the double-buffered prefetch any input pipeline does), results go back D2H.
+    copy_stream = torch.cuda.Stream()
+    dev_bufs = [{k: torch.empty_like(v) for k, v in res.items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "primed": False}
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])                 # the step that read this buffer has finished
+            for k, v in pin.items():
+                dev_bufs[slot][k].copy_(v, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def e2e_step(rows):
-        inp = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-        logits, loss = step(inp, rows)
+        slot = e2e_state["i"] & 1
+        if not e2e_state["primed"]:
+            issue_copy(slot)
+            e2e_state["primed"] = True
+        issue_copy(slot ^ 1)
+        torch.cuda.current_stream().wait_event(ready[slot])
+        logits, loss = step(dev_bufs[slot], rows)
+        consumed[slot].record()
         out_host.copy_(logits.detach(), non_blocking=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
+        e2e_state["i"] += 1
 
     def barrier():
         if world > 1:

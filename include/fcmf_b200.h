@@ -7,7 +7,7 @@
  *
  * Conventions: raw DEVICE pointers, caller-allocated outputs, row-major, leading dimensions in ELEMENTS,
  * stream-ordered on `stream` (a cudaStream_t), no implicit synchronisation, no global mutable state except
- * a per-process cache of TMA descriptors guarded by a mutex.  Every function returns 0 on success or a
+ * the launch counter and the attention-engine switch (TMA descriptors are encoded per call and passed by value).  Every function returns 0 on success or a
  * negative FCMF_ERR_* code; fcmf_last_error() returns the message of the last failure on this thread.
  * `dtype` is the storage type of activations (FCMF_F32 or FCMF_BF16); parameters that stay fp32
  * (biases, LayerNorm gamma/beta, statistics, weight gradients) are typed `float*`.
@@ -103,6 +103,8 @@ typedef struct {
   const float* bias;                                          /* [NP, heads, Lq, Lk] fp32 or NULL */
   int32_t NP, heads, dh;
   float scale;
+  int32_t causal;       /* != 0: scores of keys j > query i are REPLACED by -1e4 (masked_fill of the IAOG decoder,
+                           mm_modeling.py:115-124; applies to self- and cross-attention alike). CUDA-core engine only. */
 } fcmf_attn_desc;
 
 /* Attention engine for subsequent calls: FCMF_ENGINE_AUTO (tcgen05 for bf16, head_dim 64, no bias, 16 <= L <= 320;

@@ -25,7 +25,7 @@ class Seg(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [("q", Seg * 2), ("k", Seg * 2), ("v", Seg * 2),
                 ("mask_add", _vp), ("ld_mask", _i64), ("mask_div", _i32),
-                ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32)]
+                ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32), ("causal", _i32)]
 
 
 # name -> argtypes (every entry point returns int); must list EVERY symbol include/fcmf_b200.h declares.

@@ -55,6 +55,7 @@ attn_fwd_kernel(AttnDev a, T* __restrict__ ctx, int64_t ldctx, float* __restrict
       s *= a.scale;                                              // scale BEFORE the mask add (mm_modeling.py:204-206)
       if (madd) s += madd[j];
       if (brow) s += brow[j];
+      if (a.causal && j > i) s = -1e4f;
       pr[j] = s;
       mx = fmaxf(mx, s);
     }
@@ -121,8 +122,10 @@ attn_bwd_dq_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
       s *= a.scale;
       if (madd) s += madd[j];
       if (brow) s += brow[j];
+      const bool dead = a.causal && j > i;
+      if (dead) s = -1e4f;
       const float pj = __expf(s - l);
-      const float ds = pj * (dp - dl);
+      const float ds = dead ? 0.f : pj * (dp - dl);
       dS[j] = ds;
       if (dbias) dbias[stat * Lk + j] = ds;
     }
@@ -178,9 +181,11 @@ attn_bwd_dkv_kernel(AttnDev a, const T* __restrict__ dctx, int64_t lddctx, const
       for (int d = 0; d < dh; ++d) { s = fmaf(qr[d], kj[d], s); dp = fmaf(gr[d], vj[d], dp); }
       s = s * a.scale + mj;
       if (a.bias) s += a.bias[(stat0 + i) * Lk + j];
+      const bool dead = a.causal && j > i;
+      if (dead) s = -1e4f;
       const float pj = __expf(s - ls[i]);
       P[i] = pj;
-      dS[i] = pj * (dp - dl[i]);
+      dS[i] = dead ? 0.f : pj * (dp - dl[i]);
     }
     __syncwarp();
     T* dkrow = dk + ((int64_t)p * Lk + j) * HD + (int64_t)h * dh;
@@ -209,7 +214,7 @@ static int to_dev(const fcmf_attn_desc* d, AttnDev* o) {
   FCMF_CHECK_ARG(o->k[0].rows == o->v[0].rows && o->k[1].rows == o->v[1].rows, "attn: k/v segment rows differ");
   o->mask_add = d->mask_add; o->ld_mask = d->ld_mask; o->mask_div = d->mask_div > 0 ? d->mask_div : 1;
   o->bias = d->bias;
-  o->NP = d->NP; o->heads = d->heads; o->dh = d->dh; o->scale = d->scale;
+  o->NP = d->NP; o->heads = d->heads; o->dh = d->dh; o->scale = d->scale; o->causal = d->causal ? 1 : 0;
   o->Lq = o->q[0].rows + o->q[1].rows;
   o->Lk = o->k[0].rows + o->k[1].rows;
   FCMF_CHECK_ARG(o->NP >= 0 && o->heads > 0 && o->dh > 0 && o->dh <= 32 * AT_MAX_DPL && o->Lq > 0 && o->Lk > 0,

@@ -10,6 +10,7 @@ struct AttnDev {
   const float* mask_add; int64_t ld_mask; int mask_div;
   const float* bias;
   int NP, heads, dh, Lq, Lk;
+  int causal;             // key j > query i => score := -1e4 (masked_fill semantics of the IAOG decoder, mm_modeling.py:115-124)
   float scale;
 };
 

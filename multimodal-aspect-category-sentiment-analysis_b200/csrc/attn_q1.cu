@@ -120,7 +120,7 @@ attn_q1_bwd_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
 }
 
 bool attn_q1_supported(const AttnDev& a) {
-  if (a.Lq != 1 || a.bias != nullptr || a.Lk > Q1_MAX_LK || a.dh > Q1_MAX_DH) return false;
+  if (a.Lq != 1 || a.bias != nullptr || a.causal || a.Lk > Q1_MAX_LK || a.dh > Q1_MAX_DH) return false;
   const int vec = 8;                                               // 16-byte row loads for bf16 (4 floats for f32)
   if (a.dh % vec) return false;
   for (int s = 0; s < 2; ++s) {

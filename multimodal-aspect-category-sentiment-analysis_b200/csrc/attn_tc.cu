@@ -529,7 +529,7 @@ static bool seg_ok(const SegDev& s) {
 }
 
 bool attn_tc_supported(const AttnDev& a, int64_t ldctx, const void* ctx) {
-  if (a.dh != 64 || a.bias != nullptr) return false;
+  if (a.dh != 64 || a.bias != nullptr || a.causal) return false;
   if (a.Lq < 16 || a.Lk < 1 || a.Lk > 320 || a.Lq > 320) return false;      // NKB, NQB <= 5
   if ((ldctx % 8) || (reinterpret_cast<uintptr_t>(ctx) & 15u)) return false;
   for (int s = 0; s < 2; ++s)

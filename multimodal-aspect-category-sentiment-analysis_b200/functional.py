@@ -108,8 +108,8 @@ def layer_tail(a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: O
 class AttnPlan:
     """Static description of one folded attention launch: which tensor/columns/rows feed each segment."""
 
-    def __init__(self, NP: int, heads: int, dh: int, mask_div: int = 1):
-        self.NP, self.heads, self.dh, self.mask_div = NP, heads, dh, mask_div
+    def __init__(self, NP: int, heads: int, dh: int, mask_div: int = 1, causal: bool = False):
+        self.NP, self.heads, self.dh, self.mask_div, self.causal = NP, heads, dh, mask_div, causal
         self.roles = {"q": [], "k": [], "v": []}     # lists of (tensor_slot, col, rows, idx, inv)
 
     def add(self, role: str, slot: int, col: int, rows: int, idx: Optional[Tensor], inv: Optional[Tensor]):
@@ -130,7 +130,7 @@ def _desc(plan: AttnPlan, tensors: Sequence[Tensor], mask_add, bias):
     segs = {role: [ops.SegSpec(tensors[s], col, rows, idx) for (s, col, rows, idx, _) in plan.roles[role]]
             for role in ("q", "k", "v")}
     return ops.make_attn_desc(segs["q"], segs["k"], segs["v"], plan.NP, plan.heads, plan.dh,
-                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias)
+                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias, plan.causal)
 
 
 class _FoldedAttention(Function):
@@ -153,14 +153,15 @@ class _FoldedAttention(Function):
         want_dbias = bias is not None and ctx.needs_input_grad[2]
         dq, dk, dv, dbias = ops.attn_bwd(desc, Lq, Lk, out, _c2(dout), lse, want_dbias)
         grads: List[Optional[Tensor]] = [None] * len(tensors)
-        covered = [0] * len(tensors)
+        covered = [set() for _ in tensors]
         for role, per_problem, L in (("q", dq, Lq), ("k", dk, Lk), ("v", dv, Lk)):
             off = 0
             for (slot, col, rows, idx, inv) in plan.roles[role]:
                 t = tensors[slot]
                 if grads[slot] is None:
                     grads[slot] = torch.empty_like(t, memory_format=torch.contiguous_format)
-                covered[slot] += HD
+                again = col in covered[slot]             # e.g. keys used as values: the second write accumulates
+                covered[slot].add(col)
                 dst = grads[slot][:, col:col + HD]
                 n_groups = t.shape[0] // rows
                 if inv is None:          # one problem per group, in order
@@ -169,10 +170,10 @@ class _FoldedAttention(Function):
                 else:
                     inv_rows = _group_rows(inv, L, off, rows)
                     G = inv.shape[1]
-                ops.gather_sum_rows(per_problem, inv_rows, n_groups * rows, G, out=dst)
+                ops.gather_sum_rows(per_problem, inv_rows, n_groups * rows, G, out=dst, accumulate=again)
                 off += rows
         for slot, t in enumerate(tensors):
-            if grads[slot] is not None and covered[slot] < t.shape[1]:
+            if grads[slot] is not None and len(covered[slot]) * HD < t.shape[1]:
                 raise RuntimeError("folded_attention: every column block of a packed tensor must be used by a segment")
         return (None, None, dbias) + tuple(grads)
 

@@ -1,10 +1,10 @@
 """IAOG Seq2Seq decoder -- consumer of the fusion output (reference
 mm_modeling.py:35-132 ``Attention``, :558-613 decoder block, :615-666 ``IAOGDecoder``).
 
-Scope note: this is the first "next" row after the fusion hot path. The dense contractions (per-head projections
-folded into one GEMM, output projection, FFN, the vocabulary projection) and every LayerNorm already run on the
-fusion path's kernels; the small T x T / T x 15 score/softmax core still uses PyTorch ops and is the piece left
-to fold into ``folded_attention`` (it needs a causal-mask flag in the kernel).
+Scope note: this is the first "next" row after the fusion hot path. Every contraction (per-head projections folded
+into one GEMM, output projection, FFN, the vocabulary projection), every LayerNorm and the T x T / T x 15 attention
+cores (``folded_attention`` with the causal masked_fill flag, keys used as values) run on the fusion path's kernels.
+``attention_weights`` (a visualisation by-product in the reference) is therefore not materialised in training mode.
 
 Contract kept from the reference (each looks odd but is what checkpoints were trained with):
   * per-head weight tensors ``w_kx`` / ``w_qx`` of shape [heads, H, dh]; the projected KEYS are also the values;
@@ -39,7 +39,7 @@ class Attention(nn.Module):
         self.attention_weights = None
 
     def _project(self, x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-        """x [B,T,E] times per-head [nh,E,dh] as ONE GEMM against the [nh*dh, E] stacking -> [B, slots, T, dh].
+        """x [B,T,E] times per-head [nh,E,dh] as ONE GEMM against the [nh*dh, E] stacking -> [B*T, slots*dh].
 
         The reference pairs input ``k.repeat(nh,1,1)[n]`` (batch n % B) with weight ``w.repeat(B,1,1)[n]`` (head n % nh)
         and then places entry n = c*B + b in output slot c of batch b (mm_modeling.py:79-85, 130): slot c of batch b uses
@@ -50,7 +50,7 @@ class Attention(nn.Module):
         y = Fn.linear(x.reshape(B * T, E), w2, None).view(B, T, nh, dh)
         slot_head = (torch.arange(nh, device=x.device).view(1, nh) * B + torch.arange(B, device=x.device).view(B, 1)) % nh
         y = torch.gather(y, 2, slot_head.view(B, 1, nh, 1).expand(B, T, nh, dh))                 # [B, T, slot, dh]
-        return y.permute(0, 2, 1, 3)
+        return y.reshape(B * T, nh * dh)
 
     def forward(self, k, q, memory_len=None):
         if k.dim() == 2:
@@ -58,23 +58,28 @@ class Attention(nn.Module):
         if q.dim() == 2:
             q = q.unsqueeze(1)
         B, k_len, q_len = k.size(0), k.size(1), q.size(1)
-        kx = self._project(k, self.w_kx).float()
-        qx = self._project(q, self.w_qx).float()
-        score = torch.matmul(qx, kx.transpose(-1, -2)) / math.sqrt(self.hidden_dim)        # [B,nh,q,k]
-        if memory_len is not None:
-            if isinstance(memory_len, (list, tuple)):
-                memory_len = torch.tensor(memory_len, device=k.device)
-            if memory_len.dim() == 1:
-                keep = torch.arange(k_len, device=k.device).unsqueeze(0) < memory_len.unsqueeze(1)
-                score = score.masked_fill(~keep.view(B, 1, 1, k_len), -1e4)
-            elif memory_len.dim() == 2:
-                keep = torch.tril(torch.ones(q_len, k_len, device=k.device, dtype=torch.bool))
-                score = score.masked_fill(~keep, -1e4)
-        prob = torch.softmax(score, dim=-1)
-        # reference layout of the stored weights: [nh*B, q, k], head-major
-        self.attention_weights = prob.permute(1, 0, 2, 3).reshape(self.n_head * B, q_len, k_len)
-        out = torch.matmul(prob, kx).permute(0, 2, 1, 3).reshape(B * q_len, self.n_head * self.hidden_dim)
-        out = Fn.linear(out.to(k.dtype), self.proj.weight, self.proj.bias)
+        nh, dh = self.n_head, self.hidden_dim
+        kx = self._project(k, self.w_kx)                              # [B*k_len, nh*dh]; keys are also the values (line 129)
+        qx = self._project(q, self.w_qx)
+        if isinstance(memory_len, (list, tuple)):
+            memory_len = torch.tensor(memory_len, device=k.device)
+        if memory_len is None or memory_len.dim() == 2:
+            # training path: no mask, or the 2-D mask = tril(q_len x k_len) on self- AND cross-attention (lines 115-118):
+            # one folded launch for all (batch, slot) problems, masked_fill(-1e4) semantics in the kernel
+            plan = Fn.AttnPlan(B, nh, dh, causal=memory_len is not None) \
+                .add("q", 0, 0, q_len, None, None).add("k", 1, 0, k_len, None, None).add("v", 1, 0, k_len, None, None)
+            out = Fn.folded_attention(plan, (qx, kx), None, None)                    # [B*q_len, nh*dh], slot-major features
+            self.attention_weights = None                                            # probabilities are not materialised
+        else:
+            # 1-D valid-length mask (inference helper of the reference): small, kept on PyTorch ops
+            kx4 = kx.view(B, k_len, nh, dh).permute(0, 2, 1, 3).float()
+            qx4 = qx.view(B, q_len, nh, dh).permute(0, 2, 1, 3).float()
+            score = torch.matmul(qx4, kx4.transpose(-1, -2)) / math.sqrt(dh)
+            keep = torch.arange(k_len, device=k.device).unsqueeze(0) < memory_len.unsqueeze(1)
+            prob = torch.softmax(score.masked_fill(~keep.view(B, 1, 1, k_len), -1e4), dim=-1)
+            self.attention_weights = prob.permute(1, 0, 2, 3).reshape(nh * B, q_len, k_len)     # reference layout [nh*B, q, k]
+            out = torch.matmul(prob, kx4).permute(0, 2, 1, 3).reshape(B * q_len, nh * dh).to(k.dtype)
+        out = Fn.linear(out, self.proj.weight, self.proj.bias)
         return out.view(B, q_len, self.embed_dim), self.attention_weights
 
 

@@ -219,7 +219,7 @@ def _fill_seg(dst: Seg, s: Optional[SegSpec], esize: int) -> None:
 
 def make_attn_desc(q: Sequence[Optional[SegSpec]], k: Sequence[Optional[SegSpec]], v: Sequence[Optional[SegSpec]],
                    NP: int, heads: int, dh: int, scale: float, mask_add: Optional[Tensor], mask_div: int,
-                   bias: Optional[Tensor]) -> AttnDesc:
+                   bias: Optional[Tensor], causal: bool = False) -> AttnDesc:
     d = AttnDesc()
     esize = q[0].t.element_size()
     for i in range(2):
@@ -231,6 +231,7 @@ def make_attn_desc(q: Sequence[Optional[SegSpec]], k: Sequence[Optional[SegSpec]
     d.mask_div = mask_div
     d.bias = _p(bias)
     d.NP, d.heads, d.dh, d.scale = NP, heads, dh, float(scale)
+    d.causal = 1 if causal else 0
     return d
 
 

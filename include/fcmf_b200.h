@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FCMF_ABI_VERSION 1
+#define FCMF_ABI_VERSION 2
 
 enum { FCMF_F32 = 0, FCMF_BF16 = 1 };
 enum { FCMF_ERR_ARG = -1, FCMF_ERR_CUDA = -2, FCMF_ERR_UNSUPPORTED = -3 };
@@ -34,6 +34,22 @@ enum {
   FCMF_EPI_TANH = 2,  /* D = tanh(acc + bias)                                  mm_modeling.py:425-431       */
   FCMF_EPI_DGELU = 3  /* D = acc * dGELU/dx(aux(in))   (backward of BertIntermediate)                       */
 };
+
+/* Dropout of one site (the reference's nn.Dropout modules: mm_modeling.py:186,233,274,322, roi_modeling.py:77,
+ * fcmf_multimodal.py:17). No mask tensor exists: keep(row, col) is a pure function of (seed + *seed_dev, row, col) that the
+ * forward and the backward kernel both evaluate (csrc/common.cuh: drop_rowseed / drop_pair). p == 0 (or a NULL
+ * fcmf_dropout pointer) = off; p is quantised to multiples of 1/65536; kept values are scaled by 1/(1-p).
+ * seed_dev may be NULL; when set it is a DEVICE uint64 that the caller advances between steps (lets a replayed CUDA
+ * graph draw fresh masks). */
+typedef struct {
+  float p;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+} fcmf_dropout;
+
+/* 1 if element (row, col) of a dropout site with this p and EFFECTIVE seed (seed + *seed_dev) is kept, else 0. Host
+ * evaluation of exactly the function the kernels run (lets a caller reproduce or audit a mask without a mask tensor). */
+int fcmf_dropout_keep(float p, uint64_t seed, uint64_t row, uint32_t col);
 
 int fcmf_abi_version(void);
 const char* fcmf_last_error(void);
@@ -59,14 +75,17 @@ int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, fl
 /* ---- row-wise kernels ------------------------------------------------------------------------------ */
 /* y[m,:] = gamma * (s - mean)/sqrt(var + eps) + beta with s = x[m,:] + res[res_idx ? res_idx[m] : m, :]
  * (res may be NULL).  TF-style LayerNorm: biased variance, eps inside the sqrt (mm_modeling.py:166-171),
- * fused with the residual add of BertSelfOutput/BertOutput (mm_modeling.py:276-280, 324-328). */
+ * fused with the residual add of BertSelfOutput/BertOutput (mm_modeling.py:276-280, 324-328).
+ * With dropout (mm_modeling.py:278, 326): s = dropout(x)[m,:] + res[...]; mask element = keep(row m, column). */
 int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_idx, const float* gamma, const float* beta,
-                void* y, float* mean, float* rstd, int64_t M, int64_t H, float eps, int dtype, void* stream);
+                void* y, float* mean, float* rstd, int64_t M, int64_t H, float eps, const fcmf_dropout* drop,
+                int dtype, void* stream);
 /* ds = dLN/ds . (dy + dy_add)  (same shape as x; dy_add may be NULL: the second gradient stream of a
- * residual fan-out); dgamma/dbeta[H] accumulate (+=) in fp32. */
+ * residual fan-out); dgamma/dbeta[H] accumulate (+=) in fp32. With dropout, ds is the gradient of the residual
+ * and dx (required then, ignored otherwise) = keep * ds / (1-p) is the gradient of x. */
 int fcmf_ln_bwd(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* res_idx, const float* gamma,
-                const float* mean, const float* rstd, void* ds, float* dgamma, float* dbeta,
-                int64_t M, int64_t H, int dtype, void* stream);
+                const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta,
+                int64_t M, int64_t H, const fcmf_dropout* drop, int dtype, void* stream);
 
 /* add[b, j] = (1 - mask[b, j]) * -10000 for j < n   (fcmf_pretraining.py:53-56, 97-100, 133-136) */
 int fcmf_mask_additive(const int64_t* mask, int64_t ldmask, float* add, int64_t rows, int64_t n, void* stream);
@@ -105,6 +124,8 @@ typedef struct {
   float scale;
   int32_t causal;       /* != 0: scores of keys j > query i are REPLACED by -1e4 (masked_fill of the IAOG decoder,
                            mm_modeling.py:115-124; applies to self- and cross-attention alike). CUDA-core engine only. */
+  fcmf_dropout drop;    /* dropout on the probabilities AFTER the softmax (mm_modeling.py:213, 260; roi_modeling.py:42-43):
+                           ctx = (keep * P / (1-p)) . V; mask element = keep(row (p*heads + h)*Lq + i, column j). */
 } fcmf_attn_desc;
 
 /* Attention engine for subsequent calls: FCMF_ENGINE_AUTO (tcgen05 for bf16, head_dim 64, no bias, 16 <= L <= 320;
@@ -131,15 +152,16 @@ int fcmf_box_geometry_bwd(const float* emb, const float* wg_w, const float* wg_b
 
 /* ---- classifier head + loss (fcmf_multimodal.py:50, run_multimodal_fcmf.py:290,474-478) --------------- */
 /* logits[R,C] = pooled[R,H] . Wc[C,H]^T + bc ; loss_rows[R] = CE(logits[r], labels[r]) (label outside [0,C) is
- * ignored); probs[R,C] saved for backward.  labels/probs/loss_rows may be NULL (logits only).  C <= 32. */
+ * ignored); probs[R,C] saved for backward.  labels/probs/loss_rows may be NULL (logits only).  C <= 32.
+ * drop: dropout on `pooled` before the classifier (fcmf_multimodal.py:49), mask = keep(row r, column k). */
 int fcmf_cls_ce_fwd(const void* pooled, const float* Wc, const float* bc, const int64_t* labels,
                     float* logits, float* probs, float* loss_rows, int64_t R, int64_t H, int32_t C,
-                    int dtype, void* stream);
+                    const fcmf_dropout* drop, int dtype, void* stream);
 /* dlogits = dlogits_in if given, else (probs - onehot(labels)) * row_scale; written to dlogits_ws [R,C];
  * dpooled[R,H] in `dtype`; dWc[C,H] (+=), dbc[C] (+=) in fp32. */
 int fcmf_cls_ce_bwd(const void* pooled, const float* Wc, const float* probs, const int64_t* labels,
                     const float* dlogits_in, float row_scale, float* dlogits_ws, void* dpooled, float* dWc,
-                    float* dbc, int64_t R, int64_t H, int32_t C, int dtype, void* stream);
+                    float* dbc, int64_t R, int64_t H, int32_t C, const fcmf_dropout* drop, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,11 +11,17 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfcmf_b200.so")
 
+ABI_VERSION = 2               # FCMF_ABI_VERSION of include/fcmf_b200.h
 F32, BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_TANH, EPI_DGELU = 0, 1, 2, 3
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class Dropout(C.Structure):
+    """fcmf_dropout (include/fcmf_b200.h): p, 64-bit seed, optional DEVICE pointer to a uint64 added to the seed."""
+    _fields_ = [("p", _f32), ("seed", C.c_uint64), ("seed_dev", _vp)]
 
 
 class Seg(C.Structure):
@@ -25,17 +31,19 @@ class Seg(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [("q", Seg * 2), ("k", Seg * 2), ("v", Seg * 2),
                 ("mask_add", _vp), ("ld_mask", _i64), ("mask_div", _i32),
-                ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32), ("causal", _i32)]
+                ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32), ("causal", _i32),
+                ("drop", Dropout)]
 
 
 # name -> argtypes (every entry point returns int); must list EVERY symbol include/fcmf_b200.h declares.
 PROTOTYPES = {
     "fcmf_abi_version": [],
+    "fcmf_dropout_keep": [_f32, C.c_uint64, C.c_uint64, C.c_uint32],
     "fcmf_device_info": [C.POINTER(C.c_int)] * 3,
     "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "fcmf_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
-    "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.c_int, _vp],
-    "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.c_int, _vp],
+    "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.POINTER(Dropout), C.c_int, _vp],
+    "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(Dropout), C.c_int, _vp],
     "fcmf_mask_additive": [_vp, _i64, _vp, _i64, _i64, _vp],
     "fcmf_gather_sum_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp],
     "fcmf_dtanh": [_vp, _vp, _vp, _i64, C.c_int, _vp],
@@ -46,8 +54,8 @@ PROTOTYPES = {
     "fcmf_attn_bwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp],
     "fcmf_box_geometry_fwd": [_vp, _vp, _vp, C.POINTER(_f32), _vp, _vp, _i64, _i32, _i32, _vp],
     "fcmf_box_geometry_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
-    "fcmf_cls_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.c_int, _vp],
-    "fcmf_cls_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.c_int, _vp],
+    "fcmf_cls_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
+    "fcmf_cls_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
 }
 
 _lock = threading.Lock()
@@ -76,8 +84,8 @@ def load() -> C.CDLL:
         lib.fcmf_last_error.restype = C.c_char_p
         lib.fcmf_kernel_launches.argtypes = []
         lib.fcmf_kernel_launches.restype = C.c_longlong
-        if lib.fcmf_abi_version() != 1:
-            raise RuntimeError(f"libfcmf_b200.so ABI version {lib.fcmf_abi_version()} != 1; rebuild")
+        if lib.fcmf_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libfcmf_b200.so ABI version {lib.fcmf_abi_version()} != {ABI_VERSION}; rebuild")
         _lib = lib
     return _lib
 

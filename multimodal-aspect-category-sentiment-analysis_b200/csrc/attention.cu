@@ -42,10 +42,12 @@ attn_fwd_kernel(AttnDev a, T* __restrict__ ctx, int64_t ldctx, float* __restrict
   float* q = qs + warp * dh;
   float* pr = ps + warp * Lk;
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  const DropCfg dc = make_drop(a.drop);
   for (int i = warp; i < Lq; i += AT_WARPS) {
     const T* qrow = seg_row<T>(a.q, p, i, h, dh);
     for (int d = lane; d < dh; d += 32) q[d] = to_f(qrow[d]);
     __syncwarp();
+    const uint32_t rseed = dc.thr16 ? drop_rowseed(dc.seed, attn_drop_row(a, p, h, i)) : 0u;
     const float* brow = a.bias ? a.bias + (((int64_t)p * a.heads + h) * Lq + i) * Lk : nullptr;
     float mx = -INFINITY;
     for (int j = lane; j < Lk; j += 32) {
@@ -61,9 +63,13 @@ attn_fwd_kernel(AttnDev a, T* __restrict__ ctx, int64_t ldctx, float* __restrict
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < Lk; j += 32) { const float e = __expf(pr[j] - mx); pr[j] = e; sum += e; }
+    for (int j = lane; j < Lk; j += 32) {
+      const float e = __expf(pr[j] - mx);
+      sum += e;                                                  // the softmax denominator is taken BEFORE dropout
+      pr[j] = (dc.thr16 && !drop_keep(rseed, (uint32_t)j, dc.thr16)) ? 0.f : e;
+    }
     sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
+    const float inv = (dc.thr16 ? dc.inv_keep : 1.0f) / sum;
     __syncwarp();
     T* orow = ctx + ((int64_t)p * Lq + i) * ldctx + (int64_t)h * dh;
     for (int d = lane; d < dh; d += 32) {
@@ -97,7 +103,9 @@ attn_bwd_dq_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
   float* go = q + dh;
   float* dS = ps + warp * Lk;
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  const DropCfg dc = make_drop(a.drop);
   for (int i = warp; i < Lq; i += AT_WARPS) {
+    const uint32_t rseed = dc.thr16 ? drop_rowseed(dc.seed, attn_drop_row(a, p, h, i)) : 0u;
     const T* qrow = seg_row<T>(a.q, p, i, h, dh);
     const T* orow = ctx + ((int64_t)p * Lq + i) * ldctx + (int64_t)h * dh;
     const T* grow = dctx + ((int64_t)p * Lq + i) * lddctx + (int64_t)h * dh;
@@ -125,6 +133,7 @@ attn_bwd_dq_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
       const bool dead = a.causal && j > i;
       if (dead) s = -1e4f;
       const float pj = __expf(s - l);
+      if (dc.thr16) dp = drop_keep(rseed, (uint32_t)j, dc.thr16) ? dp * dc.inv_keep : 0.f;   // dP = mask/(1-p) * (dO . v_j)
       const float ds = dead ? 0.f : pj * (dp - dl);
       dS[j] = ds;
       if (dbias) dbias[stat * Lk + j] = ds;
@@ -168,6 +177,7 @@ attn_bwd_dkv_kernel(AttnDev a, const T* __restrict__ dctx, int64_t lddctx, const
   float* P = ps + warp * 2 * Lq;
   float* dS = P + Lq;
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  const DropCfg dc = make_drop(a.drop);
   for (int j = warp; j < Lk; j += AT_WARPS) {
     const T* krow = seg_row<T>(a.k, p, j, h, dh);
     const T* vrow = seg_row<T>(a.v, p, j, h, dh);
@@ -184,7 +194,13 @@ attn_bwd_dkv_kernel(AttnDev a, const T* __restrict__ dctx, int64_t lddctx, const
       const bool dead = a.causal && j > i;
       if (dead) s = -1e4f;
       const float pj = __expf(s - ls[i]);
-      P[i] = pj;
+      float pd = pj;                                             // dropped probability (feeds dV)
+      if (dc.thr16) {
+        const bool keep = drop_keep(drop_rowseed(dc.seed, attn_drop_row(a, p, h, i)), (uint32_t)j, dc.thr16);
+        pd = keep ? pj * dc.inv_keep : 0.f;
+        dp = keep ? dp * dc.inv_keep : 0.f;
+      }
+      P[i] = pd;
       dS[i] = dead ? 0.f : pj * (dp - dl[i]);
     }
     __syncwarp();
@@ -215,6 +231,8 @@ static int to_dev(const fcmf_attn_desc* d, AttnDev* o) {
   o->mask_add = d->mask_add; o->ld_mask = d->ld_mask; o->mask_div = d->mask_div > 0 ? d->mask_div : 1;
   o->bias = d->bias;
   o->NP = d->NP; o->heads = d->heads; o->dh = d->dh; o->scale = d->scale; o->causal = d->causal ? 1 : 0;
+  o->drop = d->drop;
+  FCMF_CHECK_ARG(drop_check(&d->drop) == 0, "attn: dropout p must be in [0, 1)");
   o->Lq = o->q[0].rows + o->q[1].rows;
   o->Lk = o->k[0].rows + o->k[1].rows;
   FCMF_CHECK_ARG(o->NP >= 0 && o->heads > 0 && o->dh > 0 && o->dh <= 32 * AT_MAX_DPL && o->Lq > 0 && o->Lk > 0,

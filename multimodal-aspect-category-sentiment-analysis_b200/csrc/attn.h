@@ -12,7 +12,13 @@ struct AttnDev {
   int NP, heads, dh, Lq, Lk;
   int causal;             // key j > query i => score := -1e4 (masked_fill semantics of the IAOG decoder, mm_modeling.py:115-124)
   float scale;
+  fcmf_dropout drop;      // dropout on the attention probabilities (mm_modeling.py:213, 260; roi_modeling.py:42-43); p == 0: off
 };
+
+// dropout row index of query i of (problem p, head h): the mask of an attention launch is keep(row, key j)
+__host__ __device__ __forceinline__ uint64_t attn_drop_row(const AttnDev& a, int p, int h, int i) {
+  return ((uint64_t)p * (uint64_t)a.heads + (uint64_t)h) * (uint64_t)a.Lq + (uint64_t)i;
+}
 
 template <typename T>
 __device__ __forceinline__ const T* seg_row(const SegDev (&s)[2], int p, int r, int h, int dh) {

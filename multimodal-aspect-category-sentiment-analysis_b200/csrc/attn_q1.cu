@@ -51,10 +51,16 @@ attn_q1_fwd_kernel(AttnDev a, T* __restrict__ ctx, int64_t ldctx, float* __restr
   }
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int j = lane; j < Lk; j += 32) { const float e = __expf(pr[j] - mx); pr[j] = e; sum += e; }
+  const DropCfg dc = make_drop(a.drop);
+  const uint32_t rseed = dc.thr16 ? drop_rowseed(dc.seed, attn_drop_row(a, p, h, 0)) : 0u;
+  for (int j = lane; j < Lk; j += 32) {
+    const float e = __expf(pr[j] - mx);
+    sum += e;                                                    // denominator before dropout
+    pr[j] = (dc.thr16 && !drop_keep(rseed, (uint32_t)j, dc.thr16)) ? 0.f : e;
+  }
   sum = warp_sum(sum);
   __syncwarp();
-  const float inv = 1.0f / sum;
+  const float inv = (dc.thr16 ? dc.inv_keep : 1.0f) / sum;
   T* orow = ctx + (int64_t)p * ldctx + (int64_t)h * dh;
   for (int d = lane; d < dh; d += 32) {
     float o = 0.f;
@@ -94,12 +100,20 @@ attn_q1_bwd_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
   __syncwarp();
   const float l = lse[(int64_t)p * a.heads + h];
   const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+  const DropCfg dc = make_drop(a.drop);
+  const uint32_t rseed = dc.thr16 ? drop_rowseed(dc.seed, attn_drop_row(a, p, h, 0)) : 0u;
   for (int j = lane; j < Lk; j += 32) {
     float s = dot_row<T>(seg_row<T>(a.k, p, j, h, dh), q, dh) * a.scale;
     if (madd) s += madd[j];
     const float pj = __expf(s - l);
-    const float dp = dot_row<T>(seg_row<T>(a.v, p, j, h, dh), go, dh);
-    P[j] = pj;
+    float dp = dot_row<T>(seg_row<T>(a.v, p, j, h, dh), go, dh);
+    float pd = pj;
+    if (dc.thr16) {
+      const bool keep = drop_keep(rseed, (uint32_t)j, dc.thr16);
+      pd = keep ? pj * dc.inv_keep : 0.f;
+      dp = keep ? dp * dc.inv_keep : 0.f;
+    }
+    P[j] = pd;                                                     // dropped probability: dV = P_drop^T . dO
     dS[j] = pj * (dp - dl) * a.scale;                              // scale folded in: dq and dk both carry it
   }
   __syncwarp();

@@ -173,12 +173,43 @@ __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
+// One-time CTA setup of the persistent kernels: mbarrier, TMEM columns. Returns the TMEM base address.
+__device__ __forceinline__ uint32_t atc_setup(AtcShared* sh, uint32_t cols) {
+  if (threadIdx.x == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
+  if ((threadIdx.x >> 5) == 0) a_tmem_alloc(&sh->tmem, cols);
+  a_tc_before();
+  __syncthreads();
+  a_tc_after();
+  return sh->tmem;
+}
+__device__ __forceinline__ void atc_teardown(uint32_t tm, uint32_t cols) {
+  a_tc_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) { a_tc_after(); a_tmem_dealloc(tm, cols); }
+}
+// drop the probabilities of columns col0 .. col0+31 of the row with seed `rseed` (dropout AFTER the softmax sum)
+__device__ __forceinline__ void drop_row32(float (&v)[32], uint32_t rseed, uint32_t col0, uint32_t thr16) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const uint32_t hsh = drop_pair(rseed, col0 + j);
+    v[j] = drop_keep_lo(hsh, thr16) ? v[j] : 0.f;
+    v[j + 1] = drop_keep_hi(hsh, thr16) ? v[j + 1] : 0.f;
+  }
+}
+
+// All three kernels are PERSISTENT: a CTA walks over work items (item = blockIdx.x + n * gridDim.x) with its mbarrier and
+// TMEM columns set up once; what an item shares between its tiles (K/V and the mask for the query-tiled kernels) is
+// staged once per item; warps whose 32 tile rows lie entirely beyond the sequence end skip the softmax arithmetic
+// (170 query rows = 128 + 42: two of the second tile's four row-warps are idle; 49 keys in a 128-row key tile: two of
+// four) -- the first version spent the same issue slots on padding as on data (ncu: issue-bound, ~50 % of slots).
+
 // ------------------------------------------------------------------------------------------- forward
+// item = (problem, head); inner loop over the 128-row query tiles.
 // smem: [Q tile 16K = P block 0 (Q is dead once S is in TMEM)][K blocks NKB*8K][V blocks NKB*8K][P blocks 1.. (NKB-1)*16K]
 //       [mask NKB*64 f32][red 2*2*128 f32][AtcShared]
-template <int NKB>
-__global__ void __launch_bounds__(ATC_THREADS, 2)
-attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __restrict__ lse, int mtiles) {
+template <int NKB, bool DROP>
+__global__ void __launch_bounds__(ATC_THREADS, (NKB == 1 ? 3 : 2))
+attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __restrict__ lse, int mtiles, int items) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = align1k(raw);
   uint8_t* Qs = sm;
@@ -193,104 +224,122 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;     // TMEM lane / tile row owned by this thread
-  const int mt = blockIdx.x % mtiles;
-  const int ph = blockIdx.x / mtiles;
-  const int p = ph / a.heads, h = ph % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE;
+  const int Lq = a.Lq, Lk = a.Lk;
   const float scale2 = a.scale * kLog2e;                        // scores are handled in the log2 domain: one FFMA + one MUFU.EX2 each
-
-  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
-  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
-  stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
-  stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
-  stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
-  cp_async_commit();
-  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
-  cp_async_wait_all();
-  a_fence_async();
-  a_tc_before();
-  __syncthreads();
-  a_tc_after();
-  const uint32_t tm = sh->tmem;
+  const uint32_t tm = atc_setup(sh, kCols);
   const uint32_t tS = tm, tO = tm + NKB * 64;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int b = 0; b < NKB; ++b) block_mma_rr(tS + b * 64, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);
-    a_commit(&sh->bar);
-  }
-  a_mbar_wait(&sh->bar, 0);
-  a_tc_after();
-
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-  float mx = -INFINITY;
+  DropCfg dc;
+  if (DROP) dc = make_drop(a.drop);
+  uint32_t parity = 0;
+
 #pragma unroll 1
-  for (int c = grp; c < NKB * 2; c += 2) {
-    uint32_t r[32];
-    a_tmem_ld32(tS + lane_addr + c * 32, r);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
-      mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale2, m4.x), fmaf(__uint_as_float(r[j + 1]), scale2, m4.y)),
-                           fmaxf(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z), fmaf(__uint_as_float(r[j + 3]), scale2, m4.w))));
-    }
-  }
-  red[grp * 128 + trow] = mx;
-  __syncthreads();
-  mx = fmaxf(red[trow], red[128 + trow]);                       // finite: at least key 0 is real and its mask is finite
-  float sum = 0.f;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int p = item / a.heads, h = item - p * a.heads;
+    // every reader of the previous item's K/V/mask (its MMAs and pass-2 loops) has finished: see the waits below
+    stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
+    stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+    const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+    for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
+
 #pragma unroll 1
-  for (int c = grp; c < NKB * 2; c += 2) {
-    uint32_t r[32];
-    float v[32];
-    a_tmem_ld32(tS + lane_addr + c * 32, r);
+    for (int mt = 0; mt < mtiles; ++mt) {
+      const int row0 = mt * ATC_TILE;
+      const int row = row0 + trow;
+      const bool wact = row0 + (warp & 3) * 32 < Lq;            // warp-uniform: any of this warp's 32 rows is a real query
+      stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
+      cp_async_commit();
+      cp_async_wait_all();
+      a_fence_async();
+      a_tc_before();
+      __syncthreads();
+      a_tc_after();
+      if (tid == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
-      v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, m4.x) - mx);
-      v[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, m4.y) - mx);
-      v[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z) - mx);
-      v[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, m4.w) - mx);
-      sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-    }
-    store_row32(Pblk(c >> 1), trow, (c & 1) * 32, v);
-  }
-  red[256 + grp * 128 + trow] = sum;
-  a_fence_async();
-  a_tc_before();
-  __syncthreads();
-  a_tc_after();
-  sum = red[256 + trow] + red[256 + 128 + trow];
-  if (tid == 0) {
-    const int ksteps_total = (Lk + 15) >> 4;
+        for (int b = 0; b < NKB; ++b) block_mma_rr(tS + b * 64, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);
+        a_commit(&sh->bar);
+      }
+      a_mbar_wait(&sh->bar, parity); parity ^= 1;
+      a_tc_after();
+
+      float mx = -INFINITY;
+      if (wact) {
+#pragma unroll 1
+        for (int c = grp; c < NKB * 2; c += 2) {
+          uint32_t r[32];
+          a_tmem_ld32(tS + lane_addr + c * 32, r);
 #pragma unroll
-    for (int b = 0; b < NKB; ++b) {
-      const int ks = min(4, ksteps_total - b * 4);
-      if (ks > 0) block_mma_rc(tO, a_smem_u32(Pblk(b)), a_smem_u32(Vs + b * ATC_BLK_BYTES), b > 0, ks);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
+            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale2, m4.x), fmaf(__uint_as_float(r[j + 1]), scale2, m4.y)),
+                                 fmaxf(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z), fmaf(__uint_as_float(r[j + 3]), scale2, m4.w))));
+          }
+        }
+        red[grp * 128 + trow] = mx;
+      }
+      __syncthreads();
+      float sum = 0.f;
+      if (wact) {
+        mx = fmaxf(red[trow], red[128 + trow]);                 // finite: at least key 0 is real and its mask is finite
+        uint32_t rseed = 0;
+        if (DROP) rseed = drop_rowseed(dc.seed, attn_drop_row(a, p, h, row));
+#pragma unroll 1
+        for (int c = grp; c < NKB * 2; c += 2) {
+          uint32_t r[32];
+          float v[32];
+          a_tmem_ld32(tS + lane_addr + c * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
+            v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, m4.x) - mx);
+            v[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, m4.y) - mx);
+            v[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z) - mx);
+            v[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, m4.w) - mx);
+            sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+          }
+          if (DROP) drop_row32(v, rseed, (uint32_t)(c * 32), dc.thr16);    // the denominator keeps the dropped terms
+          store_row32(Pblk(c >> 1), trow, (c & 1) * 32, v);
+        }
+        red[256 + grp * 128 + trow] = sum;
+      }
+      a_fence_async();
+      a_tc_before();
+      __syncthreads();
+      a_tc_after();
+      if (tid == 0) {
+        const int ksteps_total = (Lk + 15) >> 4;
+#pragma unroll
+        for (int b = 0; b < NKB; ++b) {
+          const int ks = min(4, ksteps_total - b * 4);
+          if (ks > 0) block_mma_rc(tO, a_smem_u32(Pblk(b)), a_smem_u32(Vs + b * ATC_BLK_BYTES), b > 0, ks);
+        }
+        a_commit(&sh->bar);
+      }
+      a_mbar_wait(&sh->bar, parity); parity ^= 1;              // P.V retired: Q/P, K, V and the mask may be overwritten
+      a_tc_after();
+      if (wact) {
+        sum = red[256 + trow] + red[256 + 128 + trow];
+        uint32_t r[32];
+        a_tmem_ld32(tO + lane_addr + grp * 32, r);
+        const float osc = (DROP ? dc.inv_keep : 1.0f) / sum;
+        if (row < Lq) {
+          store_out32(ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32, r, osc);
+          if (grp == 0 && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = (mx + __log2f(sum)) * 0.69314718055994530942f;   // back to natural log
+        }
+      }
+      a_tc_before();                                            // orders this tile's tcgen05.ld before the next tile's MMAs (next __syncthreads)
     }
-    a_commit(&sh->bar);
   }
-  a_mbar_wait(&sh->bar, 1);
-  a_tc_after();
-  const int row = row0 + trow;
-  {
-    uint32_t r[32];
-    a_tmem_ld32(tO + lane_addr + grp * 32, r);
-    if (row < Lq) store_out32(ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32, r, 1.0f / sum);
-  }
-  if (grp == 0 && row < Lq && lse) lse[((int64_t)p * a.heads + h) * Lq + row] = (mx + __log2f(sum)) * 0.69314718055994530942f;   // back to natural log
-  a_tc_before();
-  __syncthreads();
-  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+  atc_teardown(tm, kCols);
 }
 
 // ------------------------------------------------------------------------------------------- dQ (+ delta)
-// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][stat 128 float2][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
-template <int NKB>
+// item = (problem, head); inner loop over the 128-row query tiles, K/V/mask staged once per item.
+// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
+template <int NKB, bool DROP>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const bf16* __restrict__ dctx, int64_t lddctx,
-                  const float* __restrict__ lse, bf16* __restrict__ dq, float* __restrict__ delta, int mtiles) {
+                  const float* __restrict__ lse, bf16* __restrict__ dq, float* __restrict__ delta, int mtiles, int items) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = align1k(raw);
   uint8_t* Qs = sm;
@@ -299,125 +348,139 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
   uint8_t* Ds = Vs + NKB * ATC_BLK_BYTES;
   float* msk = reinterpret_cast<float*>(Ds + ATC_TILE_BYTES);
-  float2* stat_s = reinterpret_cast<float2*>(msk + NKB * 64);   // (lse, delta) per tile row
-  AtcShared* sh = reinterpret_cast<AtcShared*>(stat_s + 128);
+  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
   constexpr uint32_t kCols = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;
-  const int mt = blockIdx.x % mtiles;
-  const int ph = blockIdx.x / mtiles;
-  const int p = ph / a.heads, h = ph % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, row0 = mt * ATC_TILE, HD = a.heads * 64;
+  const int Lq = a.Lq, Lk = a.Lk, HD = a.heads * 64;
   const float scale2 = a.scale * kLog2e;
-
-  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
-  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
-  stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
-  stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
-  stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
-  stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
-  cp_async_commit();
-  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
-
-  // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each
-  const int row = row0 + trow;
-  const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
-  {
-    float part = 0.f;
-    if (row < Lq) {
-      const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32;
-      const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64 + grp * 32;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        Vec16<bf16> x, y;
-        x.load(o + c * 8); y.load(g + c * 8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) part = fmaf(x.v[j], y.v[j], part);
-      }
-    }
-    float* scratch = reinterpret_cast<float*>(Ds);               // dS tile is free until the first block
-    scratch[grp * 128 + trow] = part;
-  }
-  cp_async_wait_all();
-  a_fence_async();
-  a_tc_before();
-  __syncthreads();
-  a_tc_after();
-  float dl = 0.f, l = 0.f, l2 = 0.f;
-  {
-    const float* scratch = reinterpret_cast<const float*>(Ds);
-    dl = scratch[trow] + scratch[128 + trow];
-    if (row < Lq) {
-      l = lse[stat];
-      if (grp == 0) delta[stat] = dl;
-    }
-    l2 = l * kLog2e;
-  }
-  __syncthreads();                                               // scratch (aliases dS) fully read before it is rewritten
-  const uint32_t tm = sh->tmem;
+  const int nblk = (Lk + 63) >> 6;
+  const uint32_t tm = atc_setup(sh, kCols);
   const uint32_t tS = tm, tP = tm + 64, tQ = tm + 128;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  DropCfg dc;
+  if (DROP) dc = make_drop(a.drop);
   uint32_t parity = 0;
-  const int nblk = (Lk + 63) >> 6;
 
 #pragma unroll 1
-  for (int b = 0; b < nblk; ++b) {
-    if (tid == 0) {
-      block_mma_rr(tS, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);      // S_b  = Q . K_b^T
-      block_mma_rr(tP, a_smem_u32(Gs), a_smem_u32(Vs + b * ATC_BLK_BYTES), false);      // dP_b = dO . V_b^T
-      a_commit(&sh->bar);
-    }
-    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // also: the previous block's dQ MMA (reads dS) has retired
-    a_tc_after();
-    {
-      uint32_t rs[32], rp[32];
-      float v[32];
-      a_tmem_ld32(tS + lane_addr + grp * 32, rs);
-      a_tmem_ld32(tP + lane_addr + grp * 32, rp);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int p = item / a.heads, h = item - p * a.heads;
+    stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
+    stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+    const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+    for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
+
+#pragma unroll 1
+    for (int mt = 0; mt < mtiles; ++mt) {
+      const int row0 = mt * ATC_TILE;
+      const int row = row0 + trow;
+      const bool wact = row0 + (warp & 3) * 32 < Lq;
+      stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
+      stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
+      cp_async_commit();
+      // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each
+      const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
+      {
+        float part = 0.f;
+        if (row < Lq) {
+          const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32;
+          const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64 + grp * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 m4 = *reinterpret_cast<const float4*>(msk + b * 64 + grp * 32 + j);
-        const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+          for (int c = 0; c < 4; ++c) {
+            Vec16<bf16> x, y;
+            x.load(o + c * 8); y.load(g + c * 8);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float pj = ex2_approx(fmaf(__uint_as_float(rs[j + u]), scale2, mm[u]) - l2);
-          v[j + u] = (row < Lq) ? pj * (__uint_as_float(rp[j + u]) - dl) : 0.f;
+            for (int j = 0; j < 8; ++j) part = fmaf(x.v[j], y.v[j], part);
+          }
+        }
+        float* scratch = reinterpret_cast<float*>(Ds);           // the dS tile is free until the first block (its last reader, the
+        scratch[grp * 128 + trow] = part;                        // previous tile's dQ MMA, retired before that tile's epilogue)
+      }
+      cp_async_wait_all();
+      a_fence_async();
+      a_tc_before();
+      __syncthreads();
+      a_tc_after();
+      float dl = 0.f, l2 = 0.f;
+      {
+        const float* scratch = reinterpret_cast<const float*>(Ds);
+        dl = scratch[trow] + scratch[128 + trow];
+        if (row < Lq) {
+          l2 = lse[stat] * kLog2e;
+          if (grp == 0) delta[stat] = dl;
         }
       }
-      store_row32(Ds, trow, grp * 32, v);
-    }
-    a_fence_async();
-    a_tc_before();
-    __syncthreads();
-    a_tc_after();
-    if (tid == 0) {
-      const int ks = min(4, ((Lk + 15) >> 4) - b * 4);
-      block_mma_rc(tQ, a_smem_u32(Ds), a_smem_u32(Ks + b * ATC_BLK_BYTES), b > 0, ks);  // dQ += dS_b . K_b
-      if (b == nblk - 1) a_commit(&sh->bar);
+      __syncthreads();                                           // scratch (aliases dS) fully read before it is rewritten
+      uint32_t rseed = 0;
+      float keep_sc = 1.0f;
+      if (DROP) { rseed = drop_rowseed(dc.seed, attn_drop_row(a, p, h, row)); keep_sc = dc.inv_keep; }
+
+#pragma unroll 1
+      for (int b = 0; b < nblk; ++b) {
+        if (tid == 0) {
+          block_mma_rr(tS, a_smem_u32(Qs), a_smem_u32(Ks + b * ATC_BLK_BYTES), false);      // S_b  = Q . K_b^T
+          block_mma_rr(tP, a_smem_u32(Gs), a_smem_u32(Vs + b * ATC_BLK_BYTES), false);      // dP_b = dO . V_b^T
+          a_commit(&sh->bar);
+        }
+        a_mbar_wait(&sh->bar, parity); parity ^= 1;       // also: the previous block's dQ MMA (reads dS) has retired
+        a_tc_after();
+        if (wact) {                                        // rows of idle warps feed only dQ rows that are never stored
+          uint32_t rs[32], rp[32];
+          float v[32];
+          a_tmem_ld32(tS + lane_addr + grp * 32, rs);
+          a_tmem_ld32(tP + lane_addr + grp * 32, rp);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(msk + b * 64 + grp * 32 + j);
+            const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+            uint32_t h0 = 0, h1 = 0;
+            if (DROP) { h0 = drop_pair(rseed, (uint32_t)(b * 64 + grp * 32 + j)); h1 = drop_pair(rseed, (uint32_t)(b * 64 + grp * 32 + j + 2)); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float pj = ex2_approx(fmaf(__uint_as_float(rs[j + u]), scale2, mm[u]) - l2);
+              float dp = __uint_as_float(rp[j + u]);
+              if (DROP) {
+                const uint32_t hh = u < 2 ? h0 : h1;
+                const bool keep = (u & 1) ? drop_keep_hi(hh, dc.thr16) : drop_keep_lo(hh, dc.thr16);
+                dp = keep ? dp * keep_sc : 0.f;            // dP = keep/(1-p) * (dO . v_j)
+              }
+              v[j + u] = pj * (dp - dl);
+            }
+          }
+          store_row32(Ds, trow, grp * 32, v);
+        }
+        a_fence_async();
+        a_tc_before();
+        __syncthreads();
+        a_tc_after();
+        if (tid == 0) {
+          const int ks = min(4, ((Lk + 15) >> 4) - b * 4);
+          block_mma_rc(tQ, a_smem_u32(Ds), a_smem_u32(Ks + b * ATC_BLK_BYTES), b > 0, ks);  // dQ += dS_b . K_b
+          if (b == nblk - 1) a_commit(&sh->bar);
+        }
+      }
+      a_mbar_wait(&sh->bar, parity); parity ^= 1;
+      a_tc_after();
+      if (wact) {
+        uint32_t r[32];
+        a_tmem_ld32(tQ + lane_addr + grp * 32, r);
+        if (row < Lq) store_out32(dq + ((int64_t)p * Lq + row) * HD + (int64_t)h * 64 + grp * 32, r, a.scale);
+      }
+      a_tc_before();
     }
   }
-  a_mbar_wait(&sh->bar, parity);
-  a_tc_after();
-  {
-    uint32_t r[32];
-    a_tmem_ld32(tQ + lane_addr + grp * 32, r);
-    if (row < Lq) store_out32(dq + ((int64_t)p * Lq + row) * HD + (int64_t)h * 64 + grp * 32, r, a.scale);
-  }
-  a_tc_before();
-  __syncthreads();
-  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+  atc_teardown(tm, kCols);
 }
 
 // ------------------------------------------------------------------------------------------- dK, dV
-// CTA tile = 128 KEY rows; query blocks of 64 stream through a 2-stage ring (prefetched with cp.async).
-// smem: [K 16K][V 16K][ring 2 x (Q 8K | dO 8K)][P^T 16K][dS^T 16K][lse NQB*64][delta NQB*64][AtcShared]
+// item = (problem, head, 128-row KEY tile); query blocks of 64 stream through a 2-stage ring (prefetched with cp.async).
+// smem: [K 16K][V 16K][ring 2 x (Q 8K | dO 8K)][P^T 16K][dS^T 16K][lse NQB*64][delta NQB*64][row seeds NQB*64][AtcShared]
 // TMEM: S^T 64 | dP^T 64 | dV 64 | dK 64
-template <int NQB>
+template <int NQB, bool DROP>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, const float* __restrict__ lse,
-                   const float* __restrict__ delta, bf16* __restrict__ dk, bf16* __restrict__ dv, int ktiles) {
+                   const float* __restrict__ delta, bf16* __restrict__ dk, bf16* __restrict__ dv, int ktiles, int items) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = align1k(raw);
   uint8_t* Ks = sm;
@@ -427,99 +490,114 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
   uint8_t* St = Pt + ATC_TILE_BYTES;
   float* ls = reinterpret_cast<float*>(St + ATC_TILE_BYTES);
   float* dls = ls + NQB * 64;
-  AtcShared* sh = reinterpret_cast<AtcShared*>(dls + NQB * 64);
+  uint32_t* rsd = reinterpret_cast<uint32_t*>(dls + NQB * 64);   // dropout row seed of every query row
+  AtcShared* sh = reinterpret_cast<AtcShared*>(rsd + NQB * 64);
   constexpr uint32_t kCols = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = warp >> 2, trow = (warp & 3) * 32 + lane;
-  const int kt = blockIdx.x % ktiles;
-  const int ph = blockIdx.x / ktiles;
-  const int p = ph / a.heads, h = ph % a.heads;
-  const int Lq = a.Lq, Lk = a.Lk, key0 = kt * ATC_TILE, HD = a.heads * 64;
+  const int Lq = a.Lq, Lk = a.Lk, HD = a.heads * 64;
   const int nblk = (Lq + 63) >> 6;
-
-  if (tid == 0) { a_mbar_init(&sh->bar, 1); a_fence_init(); }
-  if (warp == 0) a_tmem_alloc(&sh->tmem, kCols);
-  stage_seg(Ks, a.k, p, h, key0, ATC_TILE, Lk);
-  stage_seg(Vs, a.v, p, h, key0, ATC_TILE, Lk);
-  stage_seg(ring, a.q, p, h, 0, 64, Lq);
-  stage_plain(ring + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, 0, 64, Lq);
-  cp_async_commit();
-  const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
-  for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
-    ls[i] = i < Lq ? lse[stat0 + i] * kLog2e : INFINITY;  // log2 domain; exp2(s - inf) = 0 for the padded queries
-    dls[i] = i < Lq ? delta[stat0 + i] : 0.f;
-  }
-  const int key = key0 + trow;
-  const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
-  const float mk = (key < Lk && madd) ? madd[key] * kLog2e : 0.f;
   const float scale2 = a.scale * kLog2e;
-  cp_async_wait_all();
-  a_fence_async();
-  a_tc_before();
-  __syncthreads();
-  a_tc_after();
-  const uint32_t tm = sh->tmem;
+  const uint32_t tm = atc_setup(sh, kCols);
   const uint32_t tS = tm, tP = tm + 64, tV = tm + 128, tK = tm + 192;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  DropCfg dc;
+  if (DROP) dc = make_drop(a.drop);
   uint32_t parity = 0;
 
 #pragma unroll 1
-  for (int b = 0; b < nblk; ++b) {
-    uint8_t* Qb = ring + (b & 1) * ATC_TILE_BYTES;
-    uint8_t* Gb = Qb + ATC_BLK_BYTES;
-    if (tid == 0) {
-      block_mma_rr(tS, a_smem_u32(Ks), a_smem_u32(Qb), false);                          // S^T_b  = K . Q_b^T
-      block_mma_rr(tP, a_smem_u32(Vs), a_smem_u32(Gb), false);                          // dP^T_b = V . dO_b^T
-      a_commit(&sh->bar);
-    }
-    a_mbar_wait(&sh->bar, parity); parity ^= 1;       // every earlier MMA has retired: the other ring stage and P^T/dS^T are free
-    a_tc_after();
-    if (b + 1 < nblk) {                                // prefetch the next query block while this one is processed
-      uint8_t* Qn = ring + ((b + 1) & 1) * ATC_TILE_BYTES;
-      stage_seg(Qn, a.q, p, h, (b + 1) * 64, 64, Lq);
-      stage_plain(Qn + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, (b + 1) * 64, 64, Lq);
-    }
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int kt = item % ktiles;
+    const int ph = item / ktiles;
+    const int p = ph / a.heads, h = ph - p * a.heads;
+    const int key0 = kt * ATC_TILE;
+    const int key = key0 + trow;
+    const bool wact = key0 + (warp & 3) * 32 < Lk;               // warp-uniform: any of this warp's 32 rows is a real key
+    stage_seg(Ks, a.k, p, h, key0, ATC_TILE, Lk);
+    stage_seg(Vs, a.v, p, h, key0, ATC_TILE, Lk);
+    stage_seg(ring, a.q, p, h, 0, 64, Lq);
+    stage_plain(ring + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, 0, 64, Lq);
     cp_async_commit();
-    {
-      uint32_t rs[32], rp[32];
-      float pv[32], dsv[32];
-      a_tmem_ld32(tS + lane_addr + grp * 32, rs);
-      a_tmem_ld32(tP + lane_addr + grp * 32, rp);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int qi = b * 64 + grp * 32 + j;
-        const float pj = (key < Lk) ? ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, mk) - ls[qi]) : 0.f;
-        pv[j] = pj;
-        dsv[j] = pj * (__uint_as_float(rp[j]) - dls[qi]);
-      }
-      store_row32(Pt, trow, grp * 32, pv);
-      store_row32(St, trow, grp * 32, dsv);
+    const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
+    for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
+      ls[i] = i < Lq ? lse[stat0 + i] * kLog2e : INFINITY;      // log2 domain; exp2(s - inf) = 0 for the padded queries
+      dls[i] = i < Lq ? delta[stat0 + i] : 0.f;
+      if (DROP) rsd[i] = drop_rowseed(dc.seed, attn_drop_row(a, p, h, i));
     }
+    const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
+    const float mk = (key < Lk && madd) ? madd[key] * kLog2e : 0.f;
+    const uint32_t kpair = (uint32_t)key >> 1, kshift = ((uint32_t)key & 1u) * 16u;
     cp_async_wait_all();
     a_fence_async();
     a_tc_before();
     __syncthreads();
     a_tc_after();
-    if (tid == 0) {
-      const int ks = min(4, ((Lq + 15) >> 4) - b * 4);
-      block_mma_rc(tV, a_smem_u32(Pt), a_smem_u32(Gb), b > 0, ks);                      // dV += P^T_b . dO_b
-      block_mma_rc(tK, a_smem_u32(St), a_smem_u32(Qb), b > 0, ks);                      // dK += dS^T_b . Q_b
-      if (b == nblk - 1) a_commit(&sh->bar);
-    }
-  }
-  a_mbar_wait(&sh->bar, parity);
-  a_tc_after();
+
 #pragma unroll 1
-  for (int c = grp; c < 4; c += 2) {                   // chunks 0,1 = dV columns, 2,3 = dK columns
-    uint32_t r[32];
-    a_tmem_ld32((c < 2 ? tV : tK) + lane_addr + (c & 1) * 32, r);
-    if (key < Lk)
-      store_out32((c < 2 ? dv : dk) + ((int64_t)p * Lk + key) * HD + (int64_t)h * 64 + (c & 1) * 32, r, c < 2 ? 1.0f : a.scale);
+    for (int b = 0; b < nblk; ++b) {
+      uint8_t* Qb = ring + (b & 1) * ATC_TILE_BYTES;
+      uint8_t* Gb = Qb + ATC_BLK_BYTES;
+      if (tid == 0) {
+        block_mma_rr(tS, a_smem_u32(Ks), a_smem_u32(Qb), false);                          // S^T_b  = K . Q_b^T
+        block_mma_rr(tP, a_smem_u32(Vs), a_smem_u32(Gb), false);                          // dP^T_b = V . dO_b^T
+        a_commit(&sh->bar);
+      }
+      a_mbar_wait(&sh->bar, parity); parity ^= 1;       // every earlier MMA has retired: the other ring stage and P^T/dS^T are free
+      a_tc_after();
+      if (b + 1 < nblk) {                                // prefetch the next query block while this one is processed
+        uint8_t* Qn = ring + ((b + 1) & 1) * ATC_TILE_BYTES;
+        stage_seg(Qn, a.q, p, h, (b + 1) * 64, 64, Lq);
+        stage_plain(Qn + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, (b + 1) * 64, 64, Lq);
+      }
+      cp_async_commit();
+      if (wact) {                                        // rows of idle warps feed only dK/dV rows that are never stored
+        uint32_t rs[32], rp[32];
+        float pv[32], dsv[32];
+        a_tmem_ld32(tS + lane_addr + grp * 32, rs);
+        a_tmem_ld32(tP + lane_addr + grp * 32, rp);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qi = b * 64 + grp * 32 + j;
+          const float pj = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, mk) - ls[qi]);   // 0 for padded queries (ls = +inf)
+          float pd = pj, dp = __uint_as_float(rp[j]);
+          if (DROP) {
+            const bool keep = ((mix32(rsd[qi] + kpair) >> kshift) & 0xffffu) >= dc.thr16;
+            pd = keep ? pj * dc.inv_keep : 0.f;          // dropped probability: dV = P_drop^T . dO
+            dp = keep ? dp * dc.inv_keep : 0.f;
+          }
+          pv[j] = pd;
+          dsv[j] = pj * (dp - dls[qi]);
+        }
+        store_row32(Pt, trow, grp * 32, pv);
+        store_row32(St, trow, grp * 32, dsv);
+      }
+      cp_async_wait_all();
+      a_fence_async();
+      a_tc_before();
+      __syncthreads();
+      a_tc_after();
+      if (tid == 0) {
+        const int ks = min(4, ((Lq + 15) >> 4) - b * 4);
+        block_mma_rc(tV, a_smem_u32(Pt), a_smem_u32(Gb), b > 0, ks);                      // dV += P^T_b . dO_b
+        block_mma_rc(tK, a_smem_u32(St), a_smem_u32(Qb), b > 0, ks);                      // dK += dS^T_b . Q_b
+        if (b == nblk - 1) a_commit(&sh->bar);
+      }
+    }
+    a_mbar_wait(&sh->bar, parity); parity ^= 1;          // all MMAs retired: K, V, the ring and the statistics may be overwritten
+    a_tc_after();
+    if (wact) {
+#pragma unroll 1
+      for (int c = grp; c < 4; c += 2) {                 // chunks 0,1 = dV columns, 2,3 = dK columns
+        uint32_t r[32];
+        a_tmem_ld32((c < 2 ? tV : tK) + lane_addr + (c & 1) * 32, r);
+        if (key < Lk)
+          store_out32((c < 2 ? dv : dk) + ((int64_t)p * Lk + key) * HD + (int64_t)h * 64 + (c & 1) * 32, r, c < 2 ? 1.0f : a.scale);
+      }
+    }
+    a_tc_before();
   }
-  a_tc_before();
-  __syncthreads();
-  if (warp == 0) { a_tc_after(); a_tmem_dealloc(tm, kCols); }
+  atc_teardown(tm, kCols);
 }
 
 // ------------------------------------------------------------------------------------------- host dispatch
@@ -542,6 +620,11 @@ static int set_smem_tc(K kernel, size_t bytes) {
   FCMF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return 0;
 }
+// persistent grid: every SM gets `per_sm` resident CTAs (fewer when there is less work)
+static unsigned persist_grid(int64_t items, int per_sm) {
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (unsigned)(items < cap ? items : cap);
+}
 
 #define ATC_DISPATCH(nb, CALL) \
   switch (nb) { case 1: { CALL(1); } break; case 2: { CALL(2); } break; case 3: { CALL(3); } break; \
@@ -549,13 +632,18 @@ static int set_smem_tc(K kernel, size_t bytes) {
 
 int attn_tc_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStream_t st) {
   const int nkb = (a.Lk + 63) / 64, mtiles = (a.Lq + 127) / 128;
-  const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
+  const int items = a.NP * a.heads;
+  const bool drop = a.drop.p > 0.f;
+#define LAUNCH(NB, DR)                                                                                        \
+  if (int r = set_smem_tc(attn_tc_fwd_kernel<NB, DR>, smem)) return r;                                        \
+  attn_tc_fwd_kernel<NB, DR><<<grid, ATC_THREADS, smem, st>>>(a, (bf16*)ctx, ldctx, lse, mtiles, items);
 #define CALL(NB)                                                                                              \
   const size_t smem = 1024 + (size_t)NB * (2 * ATC_BLK_BYTES + ATC_TILE_BYTES + 256) + 2048 + 64;            \
-  if (int r = set_smem_tc(attn_tc_fwd_kernel<NB>, smem)) return r;                                            \
-  attn_tc_fwd_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (bf16*)ctx, ldctx, lse, mtiles);
+  const unsigned grid = persist_grid(items, NB == 1 ? 3 : (NB <= 3 ? 2 : 1));   /* NB >= 4: 512 TMEM columns, one CTA per SM */                                                 \
+  if (drop) { LAUNCH(NB, true) } else { LAUNCH(NB, false) }
   ATC_DISPATCH(nkb, CALL)
 #undef CALL
+#undef LAUNCH
   FCMF_LAUNCH_OK();
   return 0;
 }
@@ -564,24 +652,33 @@ int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
                 float* delta, void* dq, void* dk, void* dv, cudaStream_t st) {
   const int nkb = (a.Lk + 63) / 64, nqb = (a.Lq + 63) / 64;
   const int mtiles = (a.Lq + 127) / 128, ktiles = (a.Lk + 127) / 128;
+  const bool drop = a.drop.p > 0.f;
   {
-    const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * mtiles);
+    const int items = a.NP * a.heads;
+    const unsigned grid = persist_grid(items, 2);
+#define LAUNCH(NB, DR)                                                                                        \
+    if (int r = set_smem_tc(attn_tc_dq_kernel<NB, DR>, smem)) return r;                                       \
+    attn_tc_dq_kernel<NB, DR><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse, (bf16*)dq, delta, mtiles, items);
 #define CALL(NB)                                                                                              \
-    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 1024 + 64;      \
-    if (int r = set_smem_tc(attn_tc_dq_kernel<NB>, smem)) return r;                                           \
-    attn_tc_dq_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse, (bf16*)dq, delta, mtiles);
+    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 64;             \
+    if (drop) { LAUNCH(NB, true) } else { LAUNCH(NB, false) }
     ATC_DISPATCH(nkb, CALL)
 #undef CALL
+#undef LAUNCH
     FCMF_LAUNCH_OK();
   }
   {
-    const unsigned grid = (unsigned)((int64_t)a.NP * a.heads * ktiles);
+    const int items = a.NP * a.heads * ktiles;
+    const unsigned grid = persist_grid(items, 2);
+#define LAUNCH(NB, DR)                                                                                        \
+    if (int r = set_smem_tc(attn_tc_dkv_kernel<NB, DR>, smem)) return r;                                      \
+    attn_tc_dkv_kernel<NB, DR><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)dctx, lddctx, lse, delta, (bf16*)dk, (bf16*)dv, ktiles, items);
 #define CALL(NB)                                                                                              \
-    const size_t smem = 1024 + 6 * ATC_TILE_BYTES + (size_t)NB * 512 + 64;                                   \
-    if (int r = set_smem_tc(attn_tc_dkv_kernel<NB>, smem)) return r;                                          \
-    attn_tc_dkv_kernel<NB><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)dctx, lddctx, lse, delta, (bf16*)dk, (bf16*)dv, ktiles);
+    const size_t smem = 1024 + 6 * ATC_TILE_BYTES + (size_t)NB * 768 + 64;                                   \
+    if (drop) { LAUNCH(NB, true) } else { LAUNCH(NB, false) }
     ATC_DISPATCH(nqb, CALL)
 #undef CALL
+#undef LAUNCH
     FCMF_LAUNCH_OK();
   }
   return 0;

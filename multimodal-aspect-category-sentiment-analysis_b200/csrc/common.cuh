@@ -91,6 +91,47 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- dropout: stateless counter-based masks ---------------------------------------------------------------
+// keep(row, col) is a pure function of (seed, row, col): forward and backward kernels regenerate the same mask instead
+// of storing it (no mask tensor ever touches HBM). Per row one 32-bit row seed (two rounds of an integer finaliser over
+// the 64-bit row index and seed); per PAIR of adjacent columns one more round, 16 bits per element, so p is quantised to
+// 1/65536. The effective seed is seed + *seed_dev (seed_dev may be NULL): a device-resident counter lets a replayed
+// CUDA graph draw fresh masks. tests/_util.py restates these three functions in numpy (the oracle side of the mask).
+struct DropCfg {
+  uint32_t thr16;        // drop when the element's 16-bit hash < thr16; 0 = dropout off
+  float inv_keep;        // 1 / (1 - thr16/65536)
+  uint64_t seed;
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {          // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_rowseed(uint64_t seed, uint64_t row) {
+  const uint32_t a = mix32((uint32_t)row ^ (uint32_t)seed);
+  return mix32(a ^ ((uint32_t)(row >> 32) * 0x9E3779B9U + (uint32_t)(seed >> 32)));
+}
+// 32 hash bits of the column pair (col & ~1, col | 1): low half-word = even column, high half-word = odd column
+__host__ __device__ __forceinline__ uint32_t drop_pair(uint32_t rowseed, uint32_t col) { return mix32(rowseed + (col >> 1)); }
+__host__ __device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t thr16) { return (h & 0xffffU) >= thr16; }
+__host__ __device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t thr16) { return (h >> 16) >= thr16; }
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t rowseed, uint32_t col, uint32_t thr16) {
+  const uint32_t h = drop_pair(rowseed, col);
+  return (col & 1) ? drop_keep_hi(h, thr16) : drop_keep_lo(h, thr16);
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {     // p <= 0 => 0 (off)
+  return (uint32_t)((p > 0.f ? p : 0.f) * 65536.0f + 0.5f);
+}
+__device__ __forceinline__ DropCfg make_drop(const fcmf_dropout& d) {
+  DropCfg c;
+  c.thr16 = drop_threshold(d.p);
+  c.inv_keep = 1.0f / (1.0f - (float)c.thr16 * (1.0f / 65536.0f));
+  c.seed = d.seed + (d.seed_dev ? *d.seed_dev : 0ULL);
+  return c;
+}
+inline bool drop_on(const fcmf_dropout* d) { return d != nullptr && d->p > 0.f; }
+inline int drop_check(const fcmf_dropout* d) { return (d == nullptr || (d->p >= 0.f && d->p < 1.0f)) ? 0 : -1; }
+inline fcmf_dropout drop_or_off(const fcmf_dropout* d) { return d ? *d : fcmf_dropout{0.f, 0ULL, nullptr}; }
+
 // ---- math ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) {            // mm_modeling.py:15
   return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

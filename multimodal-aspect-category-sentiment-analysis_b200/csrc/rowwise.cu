@@ -11,14 +11,18 @@ constexpr int LN_WARPS = 4;
 // Persistent warps (grid-stride over rows): gamma/beta are staged ONCE per block in shared memory -- the first version
 // re-read them per row with 2*H/32 scalar loads per lane and was LSU-issue bound (ncu: 533 warp-instructions per row,
 // 24 % of DRAM peak) -- and the next row's 16-byte loads are issued before the current row's reductions.
-template <typename T, int VPL>
+// DROP: the dense output x goes through dropout BEFORE the residual add (BertSelfOutput / BertOutput,
+// mm_modeling.py:278, 326): s = keep(row, col) * x / (1 - p) + res, mask regenerated from (seed, row, col).
+template <typename T, int VPL, bool DROP>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t* __restrict__ res_idx,
               const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
-              float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H, float eps) {
+              float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H, float eps, fcmf_dropout drop) {
   constexpr int N = Vec16<T>::N;
   extern __shared__ float ln_params[];                          // gamma[H] | beta[H]: 16-byte conflict-free reads per row
   const int lane = threadIdx.x & 31;
+  DropCfg dc;
+  if (DROP) dc = make_drop(drop);
   for (int c = threadIdx.x; c < H; c += blockDim.x) { ln_params[c] = gamma[c]; ln_params[H + c] = beta[c]; }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * LN_WARPS;
@@ -27,11 +31,21 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
     const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
     float v[VPL][N];
     float sum = 0.f;
+    uint32_t rseed = 0;
+    if (DROP) rseed = drop_rowseed(dc.seed, (uint64_t)row);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * N;
       if (c < H) {
         Vec16<T> a; a.load(xr + c);
+        if (DROP) {
+#pragma unroll
+          for (int j = 0; j < N; j += 2) {
+            const uint32_t hsh = drop_pair(rseed, (uint32_t)(c + j));
+            a.v[j] = drop_keep_lo(hsh, dc.thr16) ? a.v[j] * dc.inv_keep : 0.f;
+            a.v[j + 1] = drop_keep_hi(hsh, dc.thr16) ? a.v[j + 1] * dc.inv_keep : 0.f;
+          }
+        }
         if (rr) { Vec16<T> b; b.load(rr + c);
 #pragma unroll
           for (int j = 0; j < N; ++j) a.v[j] += b.v[j]; }
@@ -77,16 +91,20 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------- LayerNorm bwd
-template <typename T, int VPL>
+// DROP: ds (gradient of the LayerNorm input s, what the residual receives) and dx = keep * ds / (1 - p) (what the
+// dense output receives) are both written; the keep bits of a row are packed into `keep` while x is loaded.
+template <typename T, int VPL, bool DROP>
 __global__ void __launch_bounds__(LN_WARPS * 32, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* __restrict__ x, const T* __restrict__ res,
               const int32_t* __restrict__ res_idx, const float* __restrict__ gamma,
-              const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H) {
+              const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds, T* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H, fcmf_dropout drop) {
   constexpr int N = Vec16<T>::N;
   extern __shared__ float red[];                      // [LN_WARPS][2][H] column partial sums | gamma[H]
   float* gsm = red + (size_t)LN_WARPS * 2 * H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  DropCfg dc;
+  if (DROP) dc = make_drop(drop);
   for (int c = threadIdx.x; c < H; c += blockDim.x) gsm[c] = gamma[c];
   __syncthreads();
   float dg[VPL][N], db[VPL][N];
@@ -103,11 +121,27 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
     const float mu = mean[row], rs = rstd[row];
     float xh[VPL][N], gy[VPL][N];
     float s1 = 0.f, s2 = 0.f;
+    uint32_t keep[VPL];                               // bit j of keep[i]: element (i, j) of this lane survived dropout
+    uint32_t rseed = 0;
+    if (DROP) rseed = drop_rowseed(dc.seed, (uint64_t)row);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = (i * 32 + lane) * N;
+      keep[i] = 0xffffffffu;
       if (c < H) {
         Vec16<T> a, d; a.load(xr + c); d.load(dyr + c);
+        if (DROP) {
+          uint32_t kb = 0;
+#pragma unroll
+          for (int j = 0; j < N; j += 2) {
+            const uint32_t hsh = drop_pair(rseed, (uint32_t)(c + j));
+            const bool k0 = drop_keep_lo(hsh, dc.thr16), k1 = drop_keep_hi(hsh, dc.thr16);
+            a.v[j] = k0 ? a.v[j] * dc.inv_keep : 0.f;
+            a.v[j + 1] = k1 ? a.v[j + 1] * dc.inv_keep : 0.f;
+            kb |= (k0 ? 1u : 0u) << j | (k1 ? 1u : 0u) << (j + 1);
+          }
+          keep[i] = kb;
+        }
         if (dy_add) { Vec16<T> e; e.load(dy_add + row * H + c);
 #pragma unroll
           for (int j = 0; j < N; ++j) d.v[j] += e.v[j]; }
@@ -145,6 +179,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
 #pragma unroll
         for (int j = 0; j < N; ++j) o.v[j] = rs * (gy[i][j] - s1 - xh[i][j] * s2);
         o.store(dsr + c);
+        if (DROP) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) o.v[j] = ((keep[i] >> j) & 1u) ? o.v[j] * dc.inv_keep : 0.f;
+          o.store(dx + row * H + c);
+        }
       }
     }
   }
@@ -169,27 +208,37 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
 
 template <typename T, int VPL>
 static int ln_fwd_launch(const void* x, const void* res, const int32_t* idx, const float* gamma, const float* beta,
-                         void* y, float* mean, float* rstd, int64_t M, int H, float eps, cudaStream_t st) {
+                         void* y, float* mean, float* rstd, int64_t M, int H, float eps, const fcmf_dropout* drop,
+                         cudaStream_t st) {
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   const int64_t cap = (int64_t)sm_count() * 16;                 // up to 64 warps per SM, each looping over rows
   if (blocks > cap) blocks = cap;
   const unsigned grid = (unsigned)blocks;
-  ln_fwd_kernel<T, VPL><<<grid, LN_WARPS * 32, sizeof(float) * 2 * H, st>>>((const T*)x, (const T*)res, idx, gamma, beta, (T*)y, mean,
-                                                         rstd, M, H, eps);
+  if (drop_on(drop))
+    ln_fwd_kernel<T, VPL, true><<<grid, LN_WARPS * 32, sizeof(float) * 2 * H, st>>>((const T*)x, (const T*)res, idx, gamma, beta,
+                                                                                 (T*)y, mean, rstd, M, H, eps, *drop);
+  else
+    ln_fwd_kernel<T, VPL, false><<<grid, LN_WARPS * 32, sizeof(float) * 2 * H, st>>>((const T*)x, (const T*)res, idx, gamma, beta,
+                                                                                  (T*)y, mean, rstd, M, H, eps, drop_or_off(nullptr));
   FCMF_LAUNCH_OK();
   return 0;
 }
 
 template <typename T, int VPL>
 static int ln_bwd_launch(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* idx, const float* gamma,
-                         const float* mean, const float* rstd, void* ds, float* dgamma, float* dbeta, int64_t M, int H,
-                         cudaStream_t st) {
+                         const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta, int64_t M, int H,
+                         const fcmf_dropout* drop, cudaStream_t st) {
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = sizeof(float) * (LN_WARPS * 2 + 1) * H;
-  ln_bwd_kernel<T, VPL><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
-      (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, dgamma, dbeta, M, H);
+  if (drop_on(drop))
+    ln_bwd_kernel<T, VPL, true><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
+        (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, (T*)dx, dgamma, dbeta, M, H, *drop);
+  else
+    ln_bwd_kernel<T, VPL, false><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
+        (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, (T*)dx, dgamma, dbeta, M, H,
+        drop_or_off(nullptr));
   FCMF_LAUNCH_OK();
   return 0;
 }
@@ -296,29 +345,32 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_idx, const float* gamma,
                            const float* beta, void* y, float* mean, float* rstd, int64_t M, int64_t H64, float eps,
-                           int dtype, void* stream) {
+                           const fcmf_dropout* drop, int dtype, void* stream) {
   const int H = (int)H64;
   FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_fwd: bad shape");
   FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_fwd: H=%d must be a multiple of the 16-byte vector", H);
   FCMF_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)) && aligned16(gamma) && aligned16(beta), "ln_fwd: pointers must be 16-byte aligned");
+  FCMF_CHECK_ARG(drop_check(drop) == 0, "ln_fwd: dropout p must be in [0, 1)");
   if (M == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, st);
-  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, st);
+  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, drop, st);
+  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_fwd_launch, x, res, res_idx, gamma, beta, y, mean, rstd, M, H, eps, drop, st);
   return fail(FCMF_ERR_ARG, "ln_fwd: bad dtype %d", dtype);
 }
 
 extern "C" int fcmf_ln_bwd(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* res_idx, const float* gamma,
-                           const float* mean, const float* rstd, void* ds, float* dgamma, float* dbeta, int64_t M,
-                           int64_t H64, int dtype, void* stream) {
+                           const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta, int64_t M,
+                           int64_t H64, const fcmf_dropout* drop, int dtype, void* stream) {
   const int H = (int)H64;
   FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_bwd: bad shape");
   FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_bwd: H=%d must be a multiple of the 16-byte vector", H);
   FCMF_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(ds) && (!res || aligned16(res)) && (!dy_add || aligned16(dy_add)), "ln_bwd: alignment");
+  FCMF_CHECK_ARG(drop_check(drop) == 0, "ln_bwd: dropout p must be in [0, 1)");
+  FCMF_CHECK_ARG(!drop_on(drop) || (dx && aligned16(dx)), "ln_bwd: dropout needs the second output dx (16-byte aligned)");
   if (M == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dgamma, dbeta, M, H, st);
-  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dgamma, dbeta, M, H, st);
+  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, st);
+  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, st);
   return fail(FCMF_ERR_ARG, "ln_bwd: bad dtype %d", dtype);
 }
 

@@ -55,3 +55,9 @@ extern "C" int fcmf_device_info(int* sm, int* major, int* minor) {
   if (minor) *minor = p.minor;
   return 0;
 }
+
+// Host evaluation of the dropout mask the kernels regenerate on the device (same inline functions, common.cuh).
+extern "C" int fcmf_dropout_keep(float p, uint64_t seed, uint64_t row, uint32_t col) {
+  const uint32_t thr = fcmf::drop_threshold(p);
+  return fcmf::drop_keep(fcmf::drop_rowseed(seed, row), col, thr) ? 1 : 0;
+}

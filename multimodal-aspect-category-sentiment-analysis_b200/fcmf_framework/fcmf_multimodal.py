@@ -23,11 +23,16 @@ class FCMF(nn.Module):
         self.classifier = nn.Linear(M.HIDDEN_SIZE, num_labels)
 
     # ---- head: text_pooler -> (dropout) -> classifier [-> cross entropy] on the folded rows -------------------
-    def head(self, fused: torch.Tensor, labels: Optional[torch.Tensor] = None, row_scale: float = 1.0):
-        """fused [R, F, H] -> (logits [R, C] fp32, loss = row_scale * sum_r CE) ; labels None -> loss is 0."""
-        M._require_eval_or_p0(self)
+    def head(self, fused: torch.Tensor, labels: Optional[torch.Tensor] = None, row_scale: float = 1.0,
+             step_seed: Optional[int] = None):
+        """fused [R, F, H] -> (logits [R, C] fp32, loss = row_scale * sum_r CE) ; labels None -> loss is 0.
+        train() mode: dropout(p=0.1) on the pooled vector inside the classifier kernel (fcmf_multimodal.py:49)."""
+        from ..fusion import DROP_SITES
         pooled = self.text_pooler(fused)
-        return Fn.classifier_ce(pooled, self.classifier.weight, self.classifier.bias, labels, row_scale)
+        drop = None
+        if self.training:
+            drop = Fn.site_drop(Fn.new_step_seed() if step_seed is None else step_seed, DROP_SITES["head"], self.dropout_p)
+        return Fn.classifier_ce(pooled, self.classifier.weight, self.classifier.bias, labels, row_scale, drop)
 
     def forward(self, input_ids, visual_embeds_att, roi_embeds_att, roi_coors=None, token_type_ids=None,
                 attention_mask=None, added_attention_mask=None):
@@ -47,15 +52,19 @@ class FCMF(nn.Module):
                                      added_attention_mask, labels, aspects=A, rows=rows)
 
     def fuse_all_aspects(self, sequence_output, visual_embeds_att, roi_embeds_att, roi_coors, added_attention_mask,
-                         labels=None, aspects: int = 1, rows: Optional[str] = None):
-        """The fusion hot path given text-encoder states [B*A, L, H] (or [B, A, L, H])."""
+                         labels=None, aspects: int = 1, rows: Optional[str] = None, step_seed: Optional[int] = None):
+        """The fusion hot path given text-encoder states [B*A, L, H] (or [B, A, L, H]). In train() mode every dropout
+        of the reference path is applied inside the kernels; step_seed (default: drawn from torch's CPU generator)
+        determines all masks of the step."""
         if sequence_output.dim() == 4:
             aspects = sequence_output.shape[1]
             sequence_output = sequence_output.reshape(-1, *sequence_output.shape[2:])
         BA = sequence_output.shape[0]
         B = BA // aspects
+        if self.training and step_seed is None:
+            step_seed = Fn.new_step_seed()
         fused = self.encoder.fuse(sequence_output, visual_embeds_att, roi_embeds_att, roi_coors,
-                                  added_attention_mask.reshape(BA, -1), aspects=aspects, rows=rows)
+                                  added_attention_mask.reshape(BA, -1), aspects=aspects, rows=rows, step_seed=step_seed)
         lab = None if labels is None else labels.reshape(BA)
-        logits, loss = self.head(fused, lab, row_scale=1.0 / B)
+        logits, loss = self.head(fused, lab, row_scale=1.0 / B, step_seed=step_seed)
         return logits.view(B, aspects, -1), loss

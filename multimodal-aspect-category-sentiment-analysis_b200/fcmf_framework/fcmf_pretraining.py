@@ -42,17 +42,17 @@ class FCMFEncoder(nn.Module):
 
     # ---- the fusion path given text-encoder states (what the kernels cover) ---------------------------------
     def fuse(self, sequence_output, visual_embeds_att, roi_embeds_att, roi_coors, added_attention_mask,
-             aspects: int = 1, rows: Optional[str] = None):
-        """sequence_output [B*aspects, L, H] -> [B*aspects, 1+2*num_imgs, H]; visual tensors are per SAMPLE."""
+             aspects: int = 1, rows: Optional[str] = None, step_seed: Optional[int] = None):
+        """sequence_output [B*aspects, L, H] -> [B*aspects, 1+2*num_imgs, H]; visual tensors are per SAMPLE.
+        train() mode applies the reference's dropouts in the kernels; step_seed fixes the masks (tests)."""
         if roi_coors is None:
             raise ValueError("roi_coors is required (the reference dereferences it at fcmf_pretraining.py:110)")
         if added_attention_mask is None:
             raise ValueError("added_attention_mask is required (fcmf_pretraining.py:53)")
-        M._require_eval_or_p0(self.text2img_attention.layer[0].attention.output)
         dt = _compute_dtype(self, sequence_output)
         return fusion.fused_forward(self, sequence_output, visual_embeds_att, roi_embeds_att, roi_coors,
                                     added_attention_mask, aspects=aspects, rows=rows or self.rows,
-                                    engine=self.engine, compute_dtype=dt)
+                                    engine=self.engine, compute_dtype=dt, step_seed=step_seed)
 
     def forward(self, input_ids, visual_embeds_att, roi_embeds_att, roi_coors=None, token_type_ids=None,
                 attention_mask=None, added_attention_mask=None):

@@ -32,21 +32,6 @@ def _dims():
     return HIDDEN_SIZE, NUM_ATTENTION_HEADS, INTERMEDIATE_SIZE
 
 
-_DROPOUT_NOTICE_DONE = False
-
-
-def _require_eval_or_p0(module: nn.Module) -> None:
-    """The kernels implement the deterministic (dropout = identity) path, which is what parity is defined on
-    (SURVEY.md section 8(c)). In train() mode the reference applies p=0.1 dropout inside the fusion blocks; the
-    kernels do not ("known gaps"), so say so once instead of silently differing."""
-    global _DROPOUT_NOTICE_DONE
-    if module.training and float(getattr(module, "dropout_p", 0.0)) > 0.0 and not _DROPOUT_NOTICE_DONE:
-        import warnings
-        warnings.warn("fcmf_b200: the fusion kernels do not apply the reference's p=0.1 dropout in train() mode; "
-                      "outputs equal the eval()-mode fusion path (gradients still flow).", stacklevel=3)
-        _DROPOUT_NOTICE_DONE = True
-
-
 def gelu(x: torch.Tensor) -> torch.Tensor:
     """erf-GELU (reference mm_modeling.py:10-15); host-side helper, the kernels fuse it into the GEMM epilogue."""
     return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -96,14 +81,14 @@ class _QKV(nn.Module):
         self.dropout_p = ATTENTION_PROBS_DROPOUT_PROB
 
     def _attend(self, q_in: torch.Tensor, kv_in: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
-        _require_eval_or_p0(self)
         B, Lq, H = q_in.shape
         Lk = kv_in.shape[1]
         q = Fn.linear(q_in.reshape(B * Lq, H), self.query.weight, self.query.bias)
         w_kv = torch.cat((self.key.weight, self.value.weight), 0)
         b_kv = torch.cat((self.key.bias, self.value.bias), 0)
         kv = Fn.linear(kv_in.reshape(B * Lk, H), w_kv, b_kv)
-        plan = Fn.AttnPlan(B, self.num_attention_heads, self.attention_head_size) \
+        plan = Fn.AttnPlan(B, self.num_attention_heads, self.attention_head_size,
+                           drop=Fn.fresh_drop(self.dropout_p, self.training)) \
             .add("q", 0, 0, Lq, None, None).add("k", 1, 0, Lk, None, None).add("v", 1, H, Lk, None, None)
         mask_add = None
         if mask is not None:                     # the reference passes the additive [B,1,1,Lk] mask
@@ -129,25 +114,28 @@ class BertSelfOutput(nn.Module):
         self.dropout_p = HIDDEN_DROPOUT_PROB
 
     def forward(self, hidden_states, input_tensor):
-        _require_eval_or_p0(self)
         shape = input_tensor.shape
         d = Fn.linear(hidden_states.reshape(-1, hidden_states.shape[-1]), self.dense.weight, self.dense.bias)
         return _ResidualLayerNorm.apply(d, input_tensor.reshape(-1, shape[-1]).contiguous(), self.LayerNorm.weight,
-                                        self.LayerNorm.bias, self.LayerNorm.variance_epsilon).view(shape)
+                                        self.LayerNorm.bias, self.LayerNorm.variance_epsilon,
+                                        Fn.fresh_drop(self.dropout_p, self.training)).view(shape)
 
 
 class _ResidualLayerNorm(torch.autograd.Function):
+    """LN(dropout(d) + res) -- BertSelfOutput / BertOutput (reference mm_modeling.py:276-280, 324-328)."""
+
     @staticmethod
-    def forward(ctx, d, res, w, b, eps):
-        y, mean, rstd = ops.ln_fwd(d, res, None, w, b, eps)
+    def forward(ctx, d, res, w, b, eps, drop):
+        y, mean, rstd = ops.ln_fwd(d, res, None, w, b, eps, drop=drop)
+        ctx.drop = drop
         ctx.save_for_backward(d, res, w, mean, rstd)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         d, res, w, mean, rstd = ctx.saved_tensors
-        ds, dg, db = ops.ln_bwd(dy.contiguous(), None, d, res, None, w, mean, rstd)
-        return ds, ds, dg, db, None
+        ds, dd, dg, db = ops.ln_bwd_drop(dy.contiguous(), None, d, res, None, w, mean, rstd, ctx.drop)
+        return dd, ds, dg, db, None, None
 
 
 class BertAttention(nn.Module):
@@ -211,18 +199,20 @@ class BertOutput(nn.Module):
         self.dropout_p = HIDDEN_DROPOUT_PROB
 
     def forward(self, hidden_states, input_tensor):
-        _require_eval_or_p0(self)
         shape = input_tensor.shape
         d = Fn.linear(hidden_states.reshape(-1, hidden_states.shape[-1]), self.dense.weight, self.dense.bias)
         return _ResidualLayerNorm.apply(d, input_tensor.reshape(-1, shape[-1]).contiguous(), self.LayerNorm.weight,
-                                        self.LayerNorm.bias, self.LayerNorm.variance_epsilon).view(shape)
+                                        self.LayerNorm.bias, self.LayerNorm.variance_epsilon,
+                                        Fn.fresh_drop(self.dropout_p, self.training)).view(shape)
 
 
 def _tail(layer, ctx_rows, residual):
     from ..fusion import _tail_params
     shape = residual.shape
+    so, out = layer.attention.output, layer.output
     y = Fn.layer_tail(ctx_rows.reshape(-1, shape[-1]), residual.reshape(-1, shape[-1]).contiguous(), None, None,
-                      _tail_params(layer))
+                      _tail_params(layer), drop1=Fn.fresh_drop(so.dropout_p, so.training),
+                      drop2=Fn.fresh_drop(out.dropout_p, out.training))
     return y.view(shape)
 
 

@@ -34,8 +34,6 @@ class BoxMultiHeadedAttention(nn.Module):
         """q/k/v [G, NR, d_model], input_box [G, NR, 4] as (x_min, x_max, y_min, y_max) -> [G, NR, d_model]."""
         if mask is not None:
             raise NotImplementedError("FCMF never masks the ROI box attention (fcmf_pretraining.py:106-111)")
-        from .mm_modeling import _require_eval_or_p0
-        _require_eval_or_p0(self)
         G, NR, H = input_query.shape
         flat = lambda t: t.reshape(G * NR, H)
         if input_key is input_query and input_value is input_query:
@@ -48,7 +46,7 @@ class BoxMultiHeadedAttention(nn.Module):
         wg_w = torch.cat([g.weight for g in self.WGs], 0)
         wg_b = torch.cat([g.bias for g in self.WGs], 0)
         geo = Fn.box_geometry(input_box.reshape(G, NR, 4), wg_w, wg_b)
-        plan = Fn.AttnPlan(G, self.h, self.d_k).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
+        plan = Fn.AttnPlan(G, self.h, self.d_k, drop=Fn.fresh_drop(self.dropout_p, self.training)).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
             .add("v", 0, 2 * H, NR, None, None)
         x = Fn.folded_attention(plan, (qkv,), None, geo)
         if self.legacy_extra_skip:

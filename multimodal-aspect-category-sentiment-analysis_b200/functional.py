@@ -23,6 +23,41 @@ from ._lib import ENGINE_AUTO, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_TANH
 Tensor = torch.Tensor
 
 
+# ------------------------------------------------------------------------------------------------- dropout seeds
+# A dropout SITE is one nn.Dropout call of the reference. Its mask is a pure function of (site seed, row, column) that
+# the forward and backward kernels regenerate (no mask tensor); the site seed is step_seed + site_id * an odd constant.
+# step seeds come from torch's CPU generator, so torch.manual_seed() makes a training run reproducible.
+_GOLDEN64 = 0x9E3779B97F4A7C15
+_SEED_DEV: Optional[Tensor] = None            # device int64 [1] added to every seed by the kernels (CUDA-graph replay)
+
+
+def new_step_seed() -> int:
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def site_seed(step_seed: int, site: int) -> int:
+    return (step_seed + site * _GOLDEN64) & 0xFFFFFFFFFFFFFFFF
+
+
+def site_drop(step_seed: Optional[int], site: int, p: float) -> Optional[ops.Drop]:
+    """Drop description of `site` for this step; None when dropout is off (eval mode: step_seed None, or p == 0)."""
+    if step_seed is None or p <= 0.0:
+        return None
+    return ops.Drop(p, site_seed(step_seed, site), _SEED_DEV)
+
+
+def fresh_drop(p: float, training: bool) -> Optional[ops.Drop]:
+    """A site with its own fresh seed (module-level calls outside the folded path)."""
+    return ops.Drop(p, new_step_seed(), _SEED_DEV) if (training and p > 0.0) else None
+
+
+def set_seed_device_tensor(t: Optional[Tensor]) -> None:
+    """Device int64 [1] that every dropout kernel adds to its seed; graphed.py bumps it inside the captured graph so
+    that each replay draws new masks. None = off."""
+    global _SEED_DEV
+    _SEED_DEV = t
+
+
 def _c2(t: Tensor) -> Tensor:
     """2-D gradient with unit column stride (autograd may hand us expanded/strided grads)."""
     return t if (t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1) and t.stride(0) >= t.shape[1]) else t.contiguous()
@@ -63,14 +98,14 @@ class _LayerTail(Function):
 
     @staticmethod
     def forward(ctx, a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor],
-                wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2, engine: int):
+                wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2, engine: int, drop1: Optional[ops.Drop], drop2: Optional[ops.Drop]):
         dt = a.dtype
         d = ops.gemm_tn(a, ops.cast_matrix(wo, dt), bo, EPI_NONE, engine=engine)
-        x1, mean1, rstd1 = ops.ln_fwd(d, res_src, res_idx, g1, b1)
+        x1, mean1, rstd1 = ops.ln_fwd(d, res_src, res_idx, g1, b1, drop=drop1)      # LN(dropout(dense) + residual)
         g, pre = ops.gemm_tn(x1, ops.cast_matrix(w1, dt), bi1, EPI_GELU, engine=engine, want_aux=True)
         o = ops.gemm_tn(g, ops.cast_matrix(w2, dt), bi2, EPI_NONE, engine=engine)
-        y, mean2, rstd2 = ops.ln_fwd(o, x1, None, g2, b2)
-        ctx.engine = engine
+        y, mean2, rstd2 = ops.ln_fwd(o, x1, None, g2, b2, drop=drop2)
+        ctx.engine, ctx.drop1, ctx.drop2 = engine, drop1, drop2
         ctx.save_for_backward(a, res_src, res_idx, res_inv, wo, g1, w1, w2, g2, d, x1, pre, g, o, mean1, rstd1, mean2, rstd2)
         return y
 
@@ -79,37 +114,42 @@ class _LayerTail(Function):
         (a, res_src, res_idx, res_inv, wo, g1, w1, w2, g2, d, x1, pre, g, o, mean1, rstd1, mean2, rstd2) = ctx.saved_tensors
         eng, dt = ctx.engine, a.dtype
         dy = dy.contiguous()
-        ds2, dg2, db2 = ops.ln_bwd(dy, None, o, x1, None, g2, mean2, rstd2)            # grad of (o + x1)
-        dw2, dbi2 = ops.gemm_wgrad(ds2, g, engine=eng)
-        dpre = ops.gemm_tn(ds2, ops.cast_matrix(w2, dt, transpose=True), None, EPI_DGELU, aux=pre, engine=eng)
+        # ds2 = grad of s2 = dropout(o) + x1 (goes to x1), do2 = grad of o (== ds2 without dropout)
+        ds2, do2, dg2, db2 = ops.ln_bwd_drop(dy, None, o, x1, None, g2, mean2, rstd2, ctx.drop2)
+        dw2, dbi2 = ops.gemm_wgrad(do2, g, engine=eng)
+        dpre = ops.gemm_tn(do2, ops.cast_matrix(w2, dt, transpose=True), None, EPI_DGELU, aux=pre, engine=eng)
         dw1, dbi1 = ops.gemm_wgrad(dpre, x1, engine=eng)
         dx1 = ops.gemm_tn(dpre, ops.cast_matrix(w1, dt, transpose=True), None, EPI_NONE, engine=eng)
-        ds1, dg1, db1 = ops.ln_bwd(dx1, ds2, d, res_src, res_idx, g1, mean1, rstd1)    # (dx1 + ds2) through LN1
-        dwo, dbo = ops.gemm_wgrad(ds1, a, engine=eng)
-        da = ops.gemm_tn(ds1, ops.cast_matrix(wo, dt, transpose=True), None, EPI_NONE, engine=eng) if ctx.needs_input_grad[0] else None
+        # (dx1 + ds2) through LN1: ds1 = grad of s1 = dropout(d) + residual (goes to the residual), dd = grad of d
+        ds1, dd, dg1, db1 = ops.ln_bwd_drop(dx1, ds2, d, res_src, res_idx, g1, mean1, rstd1, ctx.drop1)
+        dwo, dbo = ops.gemm_wgrad(dd, a, engine=eng)
+        da = ops.gemm_tn(dd, ops.cast_matrix(wo, dt, transpose=True), None, EPI_NONE, engine=eng) if ctx.needs_input_grad[0] else None
         dres = None
         if ctx.needs_input_grad[1]:
             if res_idx is None:
                 dres = ds1
             else:
                 dres = ops.gather_sum_rows(ds1, res_inv, res_src.shape[0], res_inv.shape[1])
-        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None
+        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None, None, None
 
 
 def layer_tail(a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor], params: Sequence[Tensor],
-               engine: int = ENGINE_AUTO) -> Tensor:
+               engine: int = ENGINE_AUTO, drop1: Optional[ops.Drop] = None, drop2: Optional[ops.Drop] = None) -> Tensor:
     """params = (Wo, bo, ln1.w, ln1.b, W1, b1, W2, b2, ln2.w, ln2.b). Row m of `a` takes residual row
     res_idx[m] of res_src (identity when res_idx is None); res_inv [rows(res_src), G] lists, for every residual
-    row, the rows of `a` that used it (-1 padded) so that the backward reduction needs no atomics."""
-    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine)
+    row, the rows of `a` that used it (-1 padded) so that the backward reduction needs no atomics.
+    drop1 / drop2: hidden dropout of BertSelfOutput / BertOutput (mm_modeling.py:278, 326), mask row = row of `a`."""
+    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine, drop1, drop2)
 
 
 # ------------------------------------------------------------------------------------------------- attention
 class AttnPlan:
     """Static description of one folded attention launch: which tensor/columns/rows feed each segment."""
 
-    def __init__(self, NP: int, heads: int, dh: int, mask_div: int = 1, causal: bool = False):
+    def __init__(self, NP: int, heads: int, dh: int, mask_div: int = 1, causal: bool = False,
+                 drop: Optional[ops.Drop] = None):
         self.NP, self.heads, self.dh, self.mask_div, self.causal = NP, heads, dh, mask_div, causal
+        self.drop = drop                              # dropout on the probabilities, mask row = (p*heads + h)*Lq + i
         self.roles = {"q": [], "k": [], "v": []}     # lists of (tensor_slot, col, rows, idx, inv)
 
     def add(self, role: str, slot: int, col: int, rows: int, idx: Optional[Tensor], inv: Optional[Tensor]):
@@ -130,7 +170,7 @@ def _desc(plan: AttnPlan, tensors: Sequence[Tensor], mask_add, bias):
     segs = {role: [ops.SegSpec(tensors[s], col, rows, idx) for (s, col, rows, idx, _) in plan.roles[role]]
             for role in ("q", "k", "v")}
     return ops.make_attn_desc(segs["q"], segs["k"], segs["v"], plan.NP, plan.heads, plan.dh,
-                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias, plan.causal)
+                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias, plan.causal, plan.drop)
 
 
 class _FoldedAttention(Function):
@@ -231,9 +271,10 @@ def box_geometry(boxes: Tensor, wg_w: Tensor, wg_b: Tensor) -> Tensor:
 # ------------------------------------------------------------------------------------------------- head
 class _ClassifierCE(Function):
     @staticmethod
-    def forward(ctx, pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float):
-        logits, probs, loss_rows = ops.cls_ce_fwd(pooled.contiguous(), wc.contiguous(), bc.contiguous(), labels)
-        ctx.row_scale = row_scale
+    def forward(ctx, pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float,
+                drop: Optional[ops.Drop]):
+        logits, probs, loss_rows = ops.cls_ce_fwd(pooled.contiguous(), wc.contiguous(), bc.contiguous(), labels, drop)
+        ctx.row_scale, ctx.drop = row_scale, drop
         ctx.has_labels = labels is not None
         ctx.set_materialize_grads(False)          # an unused output arrives as None, not as a zero tensor
         ctx.save_for_backward(pooled, wc, probs, labels)
@@ -246,16 +287,18 @@ class _ClassifierCE(Function):
         pooled = pooled.contiguous()
         out = None
         if ctx.has_labels and dloss is not None:
-            dp, dw, db = ops.cls_ce_bwd(pooled, wc.contiguous(), probs, labels.to(torch.int64).contiguous(), None, ctx.row_scale)
+            dp, dw, db = ops.cls_ce_bwd(pooled, wc.contiguous(), probs, labels.to(torch.int64).contiguous(), None, ctx.row_scale, ctx.drop)
             out = [dp * dloss.to(dp.dtype), dw * dloss, db * dloss]
         if dlogits is not None:
-            dp, dw, db = ops.cls_ce_bwd(pooled, wc.contiguous(), None, None, dlogits, 1.0)
+            dp, dw, db = ops.cls_ce_bwd(pooled, wc.contiguous(), None, None, dlogits, 1.0, ctx.drop)
             out = [dp, dw, db] if out is None else [out[0] + dp, out[1] + dw, out[2] + db]
         if out is None:
-            return None, None, None, None, None
-        return out[0], out[1], out[2], None, None
+            return None, None, None, None, None, None
+        return out[0], out[1], out[2], None, None, None
 
 
-def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float = 1.0):
-    """(logits [R,C] fp32, loss scalar = row_scale * sum_r CE(logits[r], labels[r])); labels=None -> logits only."""
-    return _ClassifierCE.apply(pooled, wc, bc, labels, row_scale)
+def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float = 1.0,
+                  drop: Optional[ops.Drop] = None):
+    """(logits [R,C] fp32, loss scalar = row_scale * sum_r CE(logits[r], labels[r])); labels=None -> logits only.
+    drop: dropout on `pooled` before the classifier (fcmf_multimodal.py:49)."""
+    return _ClassifierCE.apply(pooled, wc, bc, labels, row_scale, drop)

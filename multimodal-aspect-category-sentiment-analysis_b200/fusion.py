@@ -26,6 +26,17 @@ from ._lib import ENGINE_AUTO
 Tensor = torch.Tensor
 PATCH_MASK = 49                    # fcmf_pretraining.py:53
 
+# Dropout sites of the folded path (train() mode). One site = one nn.Dropout module call of the reference, folded over
+# aspects and images: the mask of a site is keep(site seed, row, column) with the row convention noted per site.
+#   *_attn : attention probabilities (mm_modeling.py:213, 260; roi_modeling.py:42-43)   row = (problem*heads + head)*Lq + query
+#   *_out1 : BertSelfOutput hidden dropout (mm_modeling.py:278)                          row = row of the layer-tail input
+#   *_out2 : BertOutput hidden dropout (mm_modeling.py:326)                              row = row of the layer-tail input
+#   head   : FCMF.dropout on the pooled [CLS] (fcmf_multimodal.py:49)                    row = b*A + a
+# box_attn is drawn once per (sample, image) because the ROI self-attention is hoisted out of the aspect loop (the
+# reference redraws it for each of the A aspect passes); every other site has one independent draw per reference call.
+DROP_SITES = {"box_attn": 1, "t2i_attn": 2, "t2i_out1": 3, "t2i_out2": 4, "mm_attn": 5, "mm_out1": 6, "mm_out2": 7,
+              "fus_attn": 8, "fus_out1": 9, "fus_out2": 10, "head": 11}
+
 
 class _Index:
     """int32 device index tables of one (B, A, L, NI, NR, rows) configuration."""
@@ -94,9 +105,11 @@ def _tail_params(layer):
 
 def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_embeds_att: Tensor, roi_coors: Tensor,
                   added_attention_mask: Tensor, aspects: int = 1, rows: str = "full", engine: int = ENGINE_AUTO,
-                  compute_dtype: Optional[torch.dtype] = None) -> Tensor:
+                  compute_dtype: Optional[torch.dtype] = None, step_seed: Optional[int] = None) -> Tensor:
     """sequence_output [B*A, L, H] (row ba = b*A + a), visual tensors [B, ...], added_attention_mask [B*A, Lm].
-    Returns the fused sequence [B*A, 1 + 2*NI, H] of fcmf_pretraining.py:139-141 in the compute dtype."""
+    Returns the fused sequence [B*A, 1 + 2*NI, H] of fcmf_pretraining.py:139-141 in the compute dtype.
+    In train() mode the reference's dropouts are applied inside the kernels (DROP_SITES); step_seed fixes the masks
+    (default: a fresh draw from torch's CPU generator)."""
     if rows not in ("full", "live"):
         raise ValueError(f"rows must be 'full' or 'live', got {rows!r}")
     live = rows == "live"
@@ -123,6 +136,14 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
 
     t2i = enc.text2img_attention.layer[0]
     mm = enc.mm_attention.layer[0]
+    if enc.training and step_seed is None:
+        step_seed = Fn.new_step_seed()
+    if not enc.training:
+        step_seed = None
+
+    def drop(site: str, module) -> Optional[ops.Drop]:
+        return Fn.site_drop(step_seed, DROP_SITES[site], float(getattr(module, "dropout_p", 0.0)))
+
     seq2 = sequence_output.to(dt).reshape(BA * L, H)
     vis2 = visual_embeds_att[:, :NI].to(dt).reshape(B * NI * P, Dv)
     roi2 = roi_embeds_att[:, :NI].to(dt).reshape(B * NI * NR, Dv)
@@ -139,7 +160,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     wg_b = torch.cat([g.bias for g in box.WGs], 0)                                                      # [8]
     geo = Fn.box_geometry(roi_coors[:, :NI].reshape(B * NI, NR, 4), wg_w, wg_b)                         # [B*NI, 8, NR, NR]
     dkb = H // box.h
-    plan_b = Fn.AttnPlan(B * NI, box.h, dkb).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
+    plan_b = Fn.AttnPlan(B * NI, box.h, dkb, drop=drop("box_attn", box)).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
         .add("v", 0, 2 * H, NR, None, None)
     ctx_b = Fn.folded_attention(plan_b, (qkv_b,), None, geo)                                            # [B*NI*NR, H]
     rel = Fn.linear(ctx_b, box.linears[3].weight, box.linears[3].bias, engine=engine)                   # relative_roi
@@ -161,28 +182,31 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     NP = BA * NI
 
     # ---- text -> image branch, all (sample, aspect, image) problems in one launch ------------------------
-    plan1 = Fn.AttnPlan(NP, nh, dh, mask_div=NI).add("q", 0, 0, Lq, ix.p2ba, ix.ba2p) \
+    plan1 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("t2i_attn", t2i.attention.self)).add("q", 0, 0, Lq, ix.p2ba, ix.ba2p) \
         .add("k", 1, 0, P, ix.p2bi, ix.bi2p).add("v", 1, H, P, ix.p2bi, ix.bi2p)
     ctx1 = Fn.folded_attention(plan1, (q_t, kv_p), mask_add, None)                                      # [NP*Lq, H]
-    y1 = Fn.layer_tail(ctx1, seq2, ix.t2i_res_idx, ix.t2i_res_inv, _tail_params(t2i), engine=engine)
+    y1 = Fn.layer_tail(ctx1, seq2, ix.t2i_res_idx, ix.t2i_res_inv, _tail_params(t2i), engine=engine,
+                       drop1=drop("t2i_out1", t2i.attention.output), drop2=drop("t2i_out2", t2i.output))
     h_img = Fn.linear(y1.view(NP, Lq, H)[:, 0, :], enc.text2img_pooler.dense.weight, enc.text2img_pooler.dense.bias,
                       act="tanh", engine=engine)                                                        # [NP, H]
 
     # ---- text + ROI branch ---------------------------------------------------------------------------------
     if live:
-        plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI).add("q", 0, 0, 1, ix.p2ba, ix.ba2p) \
+        plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("mm_attn", mm.attention.self)).add("q", 0, 0, 1, ix.p2ba, ix.ba2p) \
             .add("k", 1, 0, L, ix.p2ba, ix.ba2p).add("k", 2, 0, NR, ix.p2bi, ix.bi2p) \
             .add("v", 1, H, L, ix.p2ba, ix.ba2p).add("v", 2, H, NR, ix.p2bi, ix.bi2p)
         ctx2 = Fn.folded_attention(plan2, (q0_mm, kv_t, kv_r), mask_add, None)                          # [NP, H]
-        y2 = Fn.layer_tail(ctx2, seq2, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine)
+        y2 = Fn.layer_tail(ctx2, seq2, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine,
+                           drop1=drop("mm_out1", mm.attention.output), drop2=drop("mm_out2", mm.output))
         Sq = 1
     else:
-        plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI)
+        plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("mm_attn", mm.attention.self))
         for role, col in (("q", 0), ("k", H), ("v", 2 * H)):
             plan2.add(role, 0, col, L, ix.p2ba, ix.ba2p).add(role, 1, col, NR, ix.p2bi, ix.bi2p)
         ctx2 = Fn.folded_attention(plan2, (qkv_t, qkv_r), mask_add, None)                               # [NP*S, H]
         text_roi = torch.cat((seq2, rel), 0)                                                            # residual rows
-        y2 = Fn.layer_tail(ctx2, text_roi, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine)
+        y2 = Fn.layer_tail(ctx2, text_roi, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine,
+                           drop1=drop("mm_out1", mm.attention.output), drop2=drop("mm_out2", mm.output))
         Sq = S
     r_img = Fn.linear(y2.view(NP, Sq, H)[:, 0, :], enc.text2roi_pooler.dense.weight, enc.text2roi_pooler.dense.bias,
                       act="tanh", engine=engine)                                                        # [NP, H]
@@ -191,8 +215,9 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     fusion = torch.cat((sequence_output.to(dt)[:, 0:1, :], h_img.view(BA, NI, H), r_img.view(BA, NI, H)), 1)
     x = fusion.reshape(BA * F, H)
     qkv_f = Fn.linear(x, w_mm, b_mm, engine=engine)
-    plan3 = Fn.AttnPlan(BA, nh, dh, mask_div=1).add("q", 0, 0, F, None, None).add("k", 0, H, F, None, None) \
+    plan3 = Fn.AttnPlan(BA, nh, dh, mask_div=1, drop=drop("fus_attn", mm.attention.self)).add("q", 0, 0, F, None, None).add("k", 0, H, F, None, None) \
         .add("v", 0, 2 * H, F, None, None)
     ctx3 = Fn.folded_attention(plan3, (qkv_f,), mask_add, None)
-    out = Fn.layer_tail(ctx3, x, None, None, _tail_params(mm), engine=engine)
+    out = Fn.layer_tail(ctx3, x, None, None, _tail_params(mm), engine=engine,
+                        drop1=drop("fus_out1", mm.attention.output), drop2=drop("fus_out2", mm.output))
     return out.view(BA, F, H)

@@ -9,12 +9,18 @@ Usage:
     step = GraphedFusionStep(model, example_inputs, aspects=6, rows="live", reducer=None)
     logits, loss = step(inputs)        # copies inputs into the static buffers, replays, returns static outputs
 Gradients land in ``param.grad`` (static tensors, overwritten every replay) and in ``step.seq_grad``.
+
+train() mode: the dropout seeds captured in the graph are immediates, so the capture also holds a device counter that
+every dropout kernel adds to its seed (fcmf_dropout.seed_dev) and that the graph itself increments first thing in
+each replay -- every replay draws fresh masks without re-capturing.
 """
 from __future__ import annotations
 
 from typing import Dict, Optional
 
 import torch
+
+from . import functional as Fn
 
 Tensor = torch.Tensor
 
@@ -25,6 +31,15 @@ class GraphedFusionStep:
         self.static = {k: v.clone() for k, v in inputs.items()}
         self.static["seq"].requires_grad_(True)
         self.params = [p for p in model.parameters() if p.requires_grad]
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.static["seq"].device) if model.training else None
+        Fn.set_seed_device_tensor(self.seed_dev)
+        try:
+            self._build(warmup)
+        finally:
+            Fn.set_seed_device_tensor(None)
+
+    def _build(self, warmup: int):
+        model = self.model
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                       # warm-up on a side stream (allocator + lazy init settle)
@@ -33,13 +48,15 @@ class GraphedFusionStep:
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if reducer is None:                                 # static gradient buffers: capture accumulates in place
+        if self.reducer is None:                            # static gradient buffers: capture accumulates in place
             for p in self.params:
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
         self.static["seq"].grad = torch.zeros_like(self.static["seq"])
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
+            if self.seed_dev is not None:
+                self.seed_dev.add_(1)                       # a new mask family per replay
             self._zero()
             self.logits, self.loss = self._run()
         self.seq_grad = self.static["seq"].grad

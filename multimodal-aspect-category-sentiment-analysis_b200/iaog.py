@@ -104,7 +104,8 @@ class AddNorm(nn.Module):
     def forward(self, X, Y):
         shape = X.shape
         return M._ResidualLayerNorm.apply(Y.reshape(-1, shape[-1]).contiguous(), X.reshape(-1, shape[-1]).contiguous(),
-                                          self.ln.weight, self.ln.bias, self.ln.variance_epsilon).view(shape)
+                                          self.ln.weight, self.ln.bias, self.ln.variance_epsilon,
+                                          Fn.fresh_drop(self.dropout_p, self.training)).view(shape)   # ln(dropout(Y) + X), :573
 
 
 class TransformerDecoderBlock(nn.Module):
@@ -145,9 +146,11 @@ class PositionalEncoding(nn.Module):
         P[:, :, 0::2] = torch.sin(X)
         P[:, :, 1::2] = torch.cos(X)
         self.register_buffer("P", P)
+        self.dropout_p = M.ATTENTION_PROBS_DROPOUT_PROB            # reference mm_modeling.py:619
 
     def forward(self, X):
-        return X + self.P[:, :X.size(1), :].to(device=X.device).type_as(X)
+        X = X + self.P[:, :X.size(1), :].to(device=X.device).type_as(X)
+        return torch.nn.functional.dropout(X, self.dropout_p, self.training)    # reference :633 (embedding side, torch RNG)
 
 
 class IAOGDecoder(nn.Module):

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/fcmf_b200.h but not exported"
     assert declared == set(pkg("_lib").exported_symbols())
-    assert lib.fcmf_abi_version() == 1
+    assert lib.fcmf_abi_version() == pkg("_lib").ABI_VERSION == int(re.search(r"#define FCMF_ABI_VERSION (\d+)", header).group(1))
 
 
 def test_state_dict_keys_match_reference_contract():
@@ -70,3 +70,28 @@ def test_flop_accounting_matches_survey_table():
     assert abs(synth.flops_forward_per_sample(d, "exec") / 1e9 - 206.70) < 0.3
     assert abs(synth.flops_forward_per_sample(d, "full") / 1e9 - 188.93) < 0.3
     assert abs(synth.flops_forward_per_sample(d, "live") / 1e9 - 5.91) < 0.3
+
+
+def test_dropout_mask_restatement_matches_the_library():
+    """oracle/dropout_mask.py (numpy) == the inline functions the kernels use, evaluated on the host by the library;
+    and the mask has the statistics of a Bernoulli(1-p) field."""
+    import numpy as np
+    from oracle import dropout_mask as DM
+    lib = pkg("_lib").load()
+    rng = np.random.RandomState(0)
+    for p in (0.1, 0.5, 0.013):
+        for _ in range(3):
+            seed = int(rng.randint(0, 2 ** 62, dtype=np.int64)) * 4 + int(rng.randint(0, 4))
+            rows = np.concatenate([rng.randint(0, 2 ** 40, size=5, dtype=np.int64), np.arange(3)])
+            m = DM.keep_mask(seed, rows, 37, p)
+            for ri, r in enumerate(rows):
+                for c in range(37):
+                    assert bool(lib.fcmf_dropout_keep(p, seed, int(r), c)) == bool(m[ri, c])
+    big = DM.keep_mask(12345, np.arange(4096), 768, 0.1)
+    assert abs(big.mean() - 0.9) < 2e-3
+    assert abs(big.mean(0) - 0.9).max() < 0.03 and abs(big.mean(1) - 0.9).max() < 0.06     # no dead rows / columns
+    a, b = big[:, 0::2], big[:, 1::2]                                                    # the two halves of a pair hash
+    assert abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 5e-3
+    assert abs(np.corrcoef(big[:-1].ravel(), big[1:].ravel())[0, 1]) < 5e-3              # adjacent rows
+    thr, inv = DM.threshold(0.1)
+    assert thr == 6554 and abs(inv - 1.0 / (1.0 - 6554 / 65536)) < 1e-6

@@ -142,14 +142,19 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {       // d/dx [x * Phi
   return cdf + x * pdf;
 }
 
-// Epilogue-rate versions for the bf16 tensor-core GEMM (the erf-GELU epilogue is issue-bound on the 8 epilogue warps:
-// ncu showed 46 warp-instructions per element with erff / __frcp_rn slow-path calls, 24 % tensor-pipe activity).
-// erf by Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 -- three orders below bf16 resolution -- with exactly one
-// MUFU.RCP and one MUFU.EX2 (raw approx instructions: no special-case subroutine, no divergence). exp(-z^2) with
-// z = x/sqrt(2) is also the Gaussian density the derivative needs, so gelu' costs no second exponential.
-__device__ __forceinline__ float rcp_approx(float x) {
+// Epilogue-rate versions for the bf16 tensor-core GEMM. The erf-GELU epilogues are bound by the MUFU pipe, not by issue
+// slots or DRAM (ncu: two MUFU per element -- RCP + EX2 of an Abramowitz-Stegun erf -- cost ~8 k cycles per 128 x 256
+// tile against 6.5 k cycles of MMA, tensor pipe 50 % active). One MUFU per element instead:
+//     Phi(x) = 0.5 (1 + erf(x / sqrt 2))  ~=  0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4)))
+// c fitted (minimax-weighted least squares over |x| <= 8, tools/fit_gelu.py) to the erf-GELU AND its derivative:
+// max |x Phi - fit| = 5.4e-5, max |d/dx - fit'| = 1.7e-4 -- below the bf16 rounding of the stored result (2^-9 relative)
+// over the range where the activation is not itself rounded to +-0 / x; MUFU.TANH adds <= 2^-11 relative on tanh.
+// x^2 is clamped at 64 (tanh has saturated to +-1 in fp32 long before; the quintic turns over at |x| = 8.06).
+// The derivative is the derivative OF THE FIT (all FMA, no second exponential), so forward and backward stay consistent.
+// fp32 parity mode never comes here: gemm_simt.cu uses erff (gelu_erf / gelu_erf_grad above).
+__device__ __forceinline__ float tanh_approx(float x) {          // MUFU.TANH
   float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -157,30 +162,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float tanh_approx(float x) {          // MUFU.TANH, rel. error ~2^-11 (< bf16 rounding)
-  float r;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
+constexpr float kGeluC0 = 0.7972415169105289f, kGeluC1 = 0.0372098378211574f, kGeluC2 = -0.0003810452660279267f;
+__device__ __forceinline__ float gelu_erf_fast(float x) {       // x * Phi(x): 6 FP32 ops + 1 MUFU
+  const float x2 = fminf(x * x, 64.0f);
+  const float t = tanh_approx(x * fmaf(fmaf(kGeluC2, x2, kGeluC1), x2, kGeluC0));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
-__device__ __forceinline__ void erf_as_parts(float x, float& erf_abs, float& gauss) {   // erf(|x|/sqrt2), exp(-x^2/2)
-  const float az = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  gauss = ex2_approx(az * az * -1.44269504088896340736f);
-  erf_abs = fmaf(-p * t, gauss, 1.0f);
-}
-__device__ __forceinline__ float gelu_erf_fast(float x) {       // x * Phi(x);  Phi(x) = 0.5 + 0.5 * sign(x) * erf(|x|/sqrt2)
-  float e, g;
-  erf_as_parts(x, e, g);
-  return fmaf(0.5f * fabsf(x), e, 0.5f * x);                    // 0.5x + 0.5|x| erf(|z|)  (sign folded into |x|)
-}
-__device__ __forceinline__ float gelu_erf_grad_fast(float x) {  // Phi(x) + x * phi(x)
-  float e, g;
-  erf_as_parts(x, e, g);
-  return fmaf(x * 0.39894228040143267794f, g, fmaf(copysignf(0.5f, x), e, 0.5f));
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {  // Phi(x) + x * phi(x) as the derivative of the fit: 12 FP32 ops + 1 MUFU
+  const float x2 = fminf(x * x, 64.0f);
+  const float t = tanh_approx(x * fmaf(fmaf(kGeluC2, x2, kGeluC1), x2, kGeluC0));
+  const float du = fmaf(fmaf(5.0f * kGeluC2, x2, 3.0f * kGeluC1), x2, kGeluC0);
+  const float sech2 = fmaf(-t, t, 1.0f);
+  return fmaf(0.5f * x * sech2, du, fmaf(0.5f, t, 0.5f));
 }
 
 }  // namespace fcmf

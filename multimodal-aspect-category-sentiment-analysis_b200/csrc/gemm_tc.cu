@@ -742,12 +742,23 @@ int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const flo
   return launch<128, false, false>(m, P, st);
 }
 
+// Split count of the weight-gradient reduction: a work unit is (tile, split) and `workers` CTAs (or CTA pairs) walk the
+// units in waves, so what matters is how full the LAST wave is. ceil(workers / tiles) -- the first version -- gave e.g.
+// 36 tiles x 3 splits = 108 units on 74 pairs (two waves, the second 46 % full: 27 % of the kernel idle) and
+// 9 tiles x 9 = 81 units (55 % efficiency). Pick the split count with the best wave efficiency, fewest splits on ties
+// (each split adds one fp32 atomic pass over the tile).
 static int pick_splits(int64_t tiles, int64_t workers, int k_blocks) {
-  int splits = (int)((workers + tiles - 1) / tiles);
-  if (splits > k_blocks) splits = k_blocks;
-  if (splits < 1) splits = 1;
-  while (splits > 1 && (int64_t)(splits - 1) * ((k_blocks + splits - 1) / splits) >= k_blocks) --splits;   // no empty split
-  return splits;
+  int best = 1;
+  double best_eff = 0.0;
+  const int max_splits = k_blocks < 32 ? k_blocks : 32;
+  for (int s = 1; s <= max_splits; ++s) {
+    if (s > 1 && (int64_t)(s - 1) * ((k_blocks + s - 1) / s) >= k_blocks) continue;      // would leave an empty split
+    const int64_t units = tiles * s;
+    const int64_t waves = (units + workers - 1) / workers;
+    const double eff = (double)units / (double)(waves * workers) - 0.004 * s;           // small cost per extra atomic pass
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
 }
 
 int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N, int64_t K,

@@ -32,10 +32,12 @@ __device__ __forceinline__ uint32_t a_smem_u32(const void* p) { return (uint32_t
 __device__ __forceinline__ void a_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a_smem_u32(bar)), "r"(count));
 }
+// suspend-time hint: the waiting threads sleep in hardware until the MMA's commit flips the phase (see gemm_tc.cu)
 __device__ __forceinline__ bool a_mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-               : "=r"(ok) : "r"(a_smem_u32(bar)), "r"(parity) : "memory");
+  const uint32_t hint_ns = 100000;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(a_smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -43,7 +45,7 @@ __device__ __forceinline__ void a_mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!a_mbar_try(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 6000000000LL) {
+    if ((++spins & 0x3f) == 0 && clock64() - t0 > 6000000000LL) {
       printf("fcmf attn_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
@@ -335,7 +337,7 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
 
 // ------------------------------------------------------------------------------------------- dQ (+ delta)
 // item = (problem, head); inner loop over the 128-row query tiles, K/V/mask staged once per item.
-// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
+// smem: [Q 16K][dO 16K][K NKB*8K][V NKB*8K][dS 16K][mask NKB*64 f32][dpart 256 f32][AtcShared]; TMEM: S 64 | dP 64 | dQ 64
 template <int NKB, bool DROP>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const bf16* __restrict__ dctx, int64_t lddctx,
@@ -348,7 +350,8 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   uint8_t* Vs = Ks + NKB * ATC_BLK_BYTES;
   uint8_t* Ds = Vs + NKB * ATC_BLK_BYTES;
   float* msk = reinterpret_cast<float*>(Ds + ATC_TILE_BYTES);
-  AtcShared* sh = reinterpret_cast<AtcShared*>(msk + NKB * 64);
+  float* dpart = msk + NKB * 64;                                 // [2 groups][128 rows] halves of delta
+  AtcShared* sh = reinterpret_cast<AtcShared*>(dpart + 256);
   constexpr uint32_t kCols = 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -378,40 +381,39 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
       const bool wact = row0 + (warp & 3) * 32 < Lq;
       stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
       stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
+      // the O tile rides in the dS buffer until the first block (its last reader, the previous tile's dQ MMA, retired
+      // before that tile's epilogue): delta is then a shared-memory dot product instead of 8 strided global loads per
+      // thread (ncu: 18 % of the kernel's stall samples sat on those loads)
+      stage_plain(Ds, ctx, ldctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
       cp_async_commit();
-      // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each
       const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
-      {
-        float part = 0.f;
-        if (row < Lq) {
-          const bf16* o = ctx + ((int64_t)p * Lq + row) * ldctx + (int64_t)h * 64 + grp * 32;
-          const bf16* g = dctx + ((int64_t)p * Lq + row) * lddctx + (int64_t)h * 64 + grp * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            Vec16<bf16> x, y;
-            x.load(o + c * 8); y.load(g + c * 8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) part = fmaf(x.v[j], y.v[j], part);
-          }
-        }
-        float* scratch = reinterpret_cast<float*>(Ds);           // the dS tile is free until the first block (its last reader, the
-        scratch[grp * 128 + trow] = part;                        // previous tile's dQ MMA, retired before that tile's epilogue)
-      }
+      float l2 = 0.f;
+      if (row < Lq) l2 = lse[stat] * kLog2e;                     // in flight while the tiles land
       cp_async_wait_all();
       a_fence_async();
       a_tc_before();
       __syncthreads();
       a_tc_after();
-      float dl = 0.f, l2 = 0.f;
       {
-        const float* scratch = reinterpret_cast<const float*>(Ds);
-        dl = scratch[trow] + scratch[128 + trow];
-        if (row < Lq) {
-          l2 = lse[stat] * kLog2e;
-          if (grp == 0) delta[stat] = dl;
+        // delta_i = dO_i . O_i : two threads per row (one per warpgroup), 32 columns each; padded rows are zero-filled
+        float part = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 wo = *reinterpret_cast<const uint4*>(Ds + swz(trow, grp * 4 + g));
+          const uint4 wg = *reinterpret_cast<const uint4*>(Gs + swz(trow, grp * 4 + g));
+          const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&wo);
+          const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&wg);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fo = __bfloat1622float2(ho[j]), fg = __bfloat1622float2(hg[j]);
+            part = fmaf(fo.x, fg.x, fmaf(fo.y, fg.y, part));
+          }
         }
+        dpart[grp * 128 + trow] = part;
       }
-      __syncthreads();                                           // scratch (aliases dS) fully read before it is rewritten
+      __syncthreads();                                           // halves exchanged; every read of the O tile (dS buffer) is done
+      const float dl = dpart[trow] + dpart[128 + trow];
+      if (row < Lq && grp == 0) delta[stat] = dl;
       uint32_t rseed = 0;
       float keep_sc = 1.0f;
       if (DROP) { rseed = drop_rowseed(dc.seed, attn_drop_row(a, p, h, row)); keep_sc = dc.inv_keep; }
@@ -660,7 +662,7 @@ int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
     if (int r = set_smem_tc(attn_tc_dq_kernel<NB, DR>, smem)) return r;                                       \
     attn_tc_dq_kernel<NB, DR><<<grid, ATC_THREADS, smem, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse, (bf16*)dq, delta, mtiles, items);
 #define CALL(NB)                                                                                              \
-    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 64;             \
+    const size_t smem = 1024 + 3 * ATC_TILE_BYTES + (size_t)NB * (2 * ATC_BLK_BYTES + 256) + 1024 + 64;      \
     if (drop) { LAUNCH(NB, true) } else { LAUNCH(NB, false) }
     ATC_DISPATCH(nkb, CALL)
 #undef CALL

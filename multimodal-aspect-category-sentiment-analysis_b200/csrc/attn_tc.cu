@@ -116,30 +116,59 @@ __device__ __forceinline__ void cp_async16(uint8_t* dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// rows [row0, row0+tile_rows) of a segmented [L x 64] bf16 matrix of (problem p, head h) -> swizzled tile; rows >= L are 0
-__device__ __forceinline__ void stage_seg(uint8_t* tile, const SegDev (&s)[2], int p, int h, int row0, int tile_rows, int L) {
-  // segment bases are per (problem, head): resolve the group indices once, not per 16-byte chunk
-  const int c = threadIdx.x & 7;
-  const int rows0 = s[0].rows;
-  const bf16* base0 = reinterpret_cast<const bf16*>(s[0].ptr) + ((int64_t)(s[0].idx ? s[0].idx[p] : p) * rows0) * s[0].ld + (int64_t)h * 64 + c * 8;
-  const bf16* base1 = s[1].rows ? reinterpret_cast<const bf16*>(s[1].ptr) + ((int64_t)(s[1].idx ? s[1].idx[p] : p) * s[1].rows) * s[1].ld + (int64_t)h * 64 + c * 8 : base0;
-  const int64_t ld0 = s[0].ld, ld1 = s[1].ld;
-  for (int r = threadIdx.x >> 3; r < tile_rows; r += ATC_THREADS / 8) {
-    const int gr = row0 + r;
-    const bool ok = gr < L;
-    const bf16* src = gr < rows0 ? base0 + gr * ld0 : base1 + (gr - rows0) * ld1;
-    cp_async16(tile + swz(r, c), ok ? src : base0, ok);
-  }
+// ---- row sources of one q/k/v operand for one (problem, head) ------------------------------------------------
+// The first version recomputed 64-bit segment addresses (and re-loaded the group indices) for every 16-byte chunk:
+// ncu attributed 26 % of the forward kernel's instructions and ~20 % of its stall samples to staging. Now: the group
+// indices of the NEXT item are fetched while the current one computes (SegIdx), the two segment base pointers are
+// formed once per item (RowSrc, the thread's 16-byte column chunk and the head offset folded in), and a thread's rows
+// (r_t + 32 k) advance by one 32-bit offset add per chunk on the common path.
+struct SegIdx { int g0, g1; };
+__device__ __forceinline__ SegIdx seg_idx(const SegDev (&s)[2], int p) {
+  SegIdx g;
+  g.g0 = s[0].idx ? s[0].idx[p] : p;
+  g.g1 = (s[1].rows && s[1].idx) ? s[1].idx[p] : p;
+  return g;
 }
-// same for a plain [NP*L, ld] activation (ctx / dctx)
-__device__ __forceinline__ void stage_plain(uint8_t* tile, const bf16* base, int64_t ld, int64_t prow0, int h, int row0,
-                                            int tile_rows, int L) {
-  const int c = threadIdx.x & 7;
-  const bf16* b0 = base + prow0 * ld + (int64_t)h * 64 + c * 8;
-  for (int r = threadIdx.x >> 3; r < tile_rows; r += ATC_THREADS / 8) {
-    const int gr = row0 + r;
+struct RowSrc {
+  const uint8_t* b0;          // row 0 of segment 0 (+ head, + this thread's chunk)
+  const uint8_t* b1;          // row 0 of segment 1 (== b0 when the segment is absent)
+  uint32_t ldb0, ldb1;        // row strides in BYTES
+  int rows0;                  // rows in segment 0
+};
+__device__ __forceinline__ RowSrc row_src(const SegDev (&s)[2], SegIdx g, int h) {
+  RowSrc r;
+  const int64_t col = (int64_t)h * 64 + (threadIdx.x & 7) * 8;
+  r.rows0 = s[0].rows;
+  r.ldb0 = (uint32_t)s[0].ld * 2u;
+  r.b0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<const bf16*>(s[0].ptr) + (int64_t)g.g0 * s[0].rows * s[0].ld + col);
+  if (s[1].rows) {
+    r.ldb1 = (uint32_t)s[1].ld * 2u;
+    r.b1 = reinterpret_cast<const uint8_t*>(reinterpret_cast<const bf16*>(s[1].ptr) + (int64_t)g.g1 * s[1].rows * s[1].ld + col);
+  } else { r.ldb1 = r.ldb0; r.b1 = r.b0; }
+  return r;
+}
+__device__ __forceinline__ RowSrc row_src_plain(const bf16* base, int64_t ld, int64_t prow0, int h) {   // [NP*L, ld] activation
+  RowSrc r;
+  r.rows0 = 0x7fffffff;
+  r.ldb0 = r.ldb1 = (uint32_t)ld * 2u;
+  r.b0 = r.b1 = reinterpret_cast<const uint8_t*>(base + prow0 * ld + (int64_t)h * 64 + (threadIdx.x & 7) * 8);
+  return r;
+}
+// rows [row0, row0+tile_rows) of the operand -> 128B-swizzled tile (row r at r*128, chunk c at c ^ (r & 7)); rows >= L are 0
+__device__ __forceinline__ void stage_rows(uint8_t* tile, const RowSrc& src, int row0, int tile_rows, int L) {
+  const int r_t = threadIdx.x >> 3;                              // this thread's first tile row; its rows are r_t + 32 k
+  uint8_t* dst = tile + r_t * 128 + ((((int)threadIdx.x & 7) ^ (r_t & 7)) << 4);      // (r & 7) is the same for all of them
+  int gr = row0 + r_t;
+  const int end = row0 + tile_rows;
+  const int fast_end = min(min(src.rows0, L), end);              // rows of segment 0 that exist
+  uint32_t off = (uint32_t)gr * src.ldb0;
+  const uint32_t step = (uint32_t)(ATC_THREADS / 8) * src.ldb0;
+  for (; gr < fast_end; gr += ATC_THREADS / 8, dst += (ATC_THREADS / 8) * 128, off += step)
+    cp_async16(dst, src.b0 + off, true);
+  for (; gr < end; gr += ATC_THREADS / 8, dst += (ATC_THREADS / 8) * 128) {            // segment 1 rows and the zero padding
     const bool ok = gr < L;
-    cp_async16(tile + swz(r, c), ok ? b0 + gr * ld : base, ok);
+    const uint8_t* sp = gr < src.rows0 ? src.b0 + (uint32_t)gr * src.ldb0 : src.b1 + (uint32_t)(gr - src.rows0) * src.ldb1;
+    cp_async16(dst, ok ? sp : src.b0, ok);
   }
 }
 // thread-owned row: write 32 consecutive bf16 (cols c0..c0+31 of a 64-col block) of row r into a swizzled tile
@@ -234,13 +263,20 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
   DropCfg dc;
   if (DROP) dc = make_drop(a.drop);
   uint32_t parity = 0;
+  SegIdx gq, gk, gv;                                            // group indices, fetched one item ahead
+  if ((int)blockIdx.x < items) { const int p0 = blockIdx.x / a.heads; gq = seg_idx(a.q, p0); gk = seg_idx(a.k, p0); gv = seg_idx(a.v, p0); }
 
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int p = item / a.heads, h = item - p * a.heads;
+    const RowSrc qsrc = row_src(a.q, gq, h);
     // every reader of the previous item's K/V/mask (its MMAs and pass-2 loops) has finished: see the waits below
-    stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
-    stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+    stage_rows(Ks, row_src(a.k, gk, h), 0, NKB * 64, Lk);
+    stage_rows(Vs, row_src(a.v, gv, h), 0, NKB * 64, Lk);
+    if (item + (int)gridDim.x < items) {
+      const int pn = (item + (int)gridDim.x) / a.heads;
+      gq = seg_idx(a.q, pn); gk = seg_idx(a.k, pn); gv = seg_idx(a.v, pn);
+    }
     const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
     for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
 
@@ -249,7 +285,7 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
       const int row0 = mt * ATC_TILE;
       const int row = row0 + trow;
       const bool wact = row0 + (warp & 3) * 32 < Lq;            // warp-uniform: any of this warp's 32 rows is a real query
-      stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
+      stage_rows(Qs, qsrc, row0, ATC_TILE, Lq);
       cp_async_commit();
       cp_async_wait_all();
       a_fence_async();
@@ -365,12 +401,19 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
   DropCfg dc;
   if (DROP) dc = make_drop(a.drop);
   uint32_t parity = 0;
+  SegIdx gq, gk, gv;                                             // group indices, fetched one item ahead
+  if ((int)blockIdx.x < items) { const int p0 = blockIdx.x / a.heads; gq = seg_idx(a.q, p0); gk = seg_idx(a.k, p0); gv = seg_idx(a.v, p0); }
 
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int p = item / a.heads, h = item - p * a.heads;
-    stage_seg(Ks, a.k, p, h, 0, NKB * 64, Lk);
-    stage_seg(Vs, a.v, p, h, 0, NKB * 64, Lk);
+    const RowSrc qsrc = row_src(a.q, gq, h);
+    stage_rows(Ks, row_src(a.k, gk, h), 0, NKB * 64, Lk);
+    stage_rows(Vs, row_src(a.v, gv, h), 0, NKB * 64, Lk);
+    if (item + (int)gridDim.x < items) {
+      const int pn = (item + (int)gridDim.x) / a.heads;
+      gq = seg_idx(a.q, pn); gk = seg_idx(a.k, pn); gv = seg_idx(a.v, pn);
+    }
     const float* madd = a.mask_add ? a.mask_add + (int64_t)(p / a.mask_div) * a.ld_mask : nullptr;
     for (int j = tid; j < NKB * 64; j += ATC_THREADS) msk[j] = j < Lk ? (madd ? madd[j] * kLog2e : 0.f) : -INFINITY;   // log2 domain
 
@@ -379,12 +422,12 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
       const int row0 = mt * ATC_TILE;
       const int row = row0 + trow;
       const bool wact = row0 + (warp & 3) * 32 < Lq;
-      stage_seg(Qs, a.q, p, h, row0, ATC_TILE, Lq);
-      stage_plain(Gs, dctx, lddctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
+      stage_rows(Qs, qsrc, row0, ATC_TILE, Lq);
+      stage_rows(Gs, row_src_plain(dctx, lddctx, (int64_t)p * Lq, h), row0, ATC_TILE, Lq);
       // the O tile rides in the dS buffer until the first block (its last reader, the previous tile's dQ MMA, retired
       // before that tile's epilogue): delta is then a shared-memory dot product instead of 8 strided global loads per
       // thread (ncu: 18 % of the kernel's stall samples sat on those loads)
-      stage_plain(Ds, ctx, ldctx, (int64_t)p * Lq, h, row0, ATC_TILE, Lq);
+      stage_rows(Ds, row_src_plain(ctx, ldctx, (int64_t)p * Lq, h), row0, ATC_TILE, Lq);
       cp_async_commit();
       const int64_t stat = ((int64_t)p * a.heads + h) * Lq + row;
       float l2 = 0.f;
@@ -507,20 +550,28 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
   DropCfg dc;
   if (DROP) dc = make_drop(a.drop);
   uint32_t parity = 0;
+  SegIdx gq, gk, gv;                                             // group indices, fetched one item ahead
+  if ((int)blockIdx.x < items) { const int p0 = (blockIdx.x / ktiles) / a.heads; gq = seg_idx(a.q, p0); gk = seg_idx(a.k, p0); gv = seg_idx(a.v, p0); }
 
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int kt = item % ktiles;
     const int ph = item / ktiles;
     const int p = ph / a.heads, h = ph - p * a.heads;
+    const RowSrc qsrc = row_src(a.q, gq, h);
+    const RowSrc gsrc = row_src_plain(dctx, lddctx, (int64_t)p * Lq, h);
     const int key0 = kt * ATC_TILE;
     const int key = key0 + trow;
     const bool wact = key0 + (warp & 3) * 32 < Lk;               // warp-uniform: any of this warp's 32 rows is a real key
-    stage_seg(Ks, a.k, p, h, key0, ATC_TILE, Lk);
-    stage_seg(Vs, a.v, p, h, key0, ATC_TILE, Lk);
-    stage_seg(ring, a.q, p, h, 0, 64, Lq);
-    stage_plain(ring + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, 0, 64, Lq);
+    stage_rows(Ks, row_src(a.k, gk, h), key0, ATC_TILE, Lk);
+    stage_rows(Vs, row_src(a.v, gv, h), key0, ATC_TILE, Lk);
+    stage_rows(ring, qsrc, 0, 64, Lq);
+    stage_rows(ring + ATC_BLK_BYTES, gsrc, 0, 64, Lq);
     cp_async_commit();
+    if (item + (int)gridDim.x < items) {
+      const int pn = ((item + (int)gridDim.x) / ktiles) / a.heads;
+      gq = seg_idx(a.q, pn); gk = seg_idx(a.k, pn); gv = seg_idx(a.v, pn);
+    }
     const int64_t stat0 = ((int64_t)p * a.heads + h) * Lq;
     for (int i = tid; i < NQB * 64; i += ATC_THREADS) {
       ls[i] = i < Lq ? lse[stat0 + i] * kLog2e : INFINITY;      // log2 domain; exp2(s - inf) = 0 for the padded queries
@@ -549,8 +600,8 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
       a_tc_after();
       if (b + 1 < nblk) {                                // prefetch the next query block while this one is processed
         uint8_t* Qn = ring + ((b + 1) & 1) * ATC_TILE_BYTES;
-        stage_seg(Qn, a.q, p, h, (b + 1) * 64, 64, Lq);
-        stage_plain(Qn + ATC_BLK_BYTES, dctx, lddctx, (int64_t)p * Lq, h, (b + 1) * 64, 64, Lq);
+        stage_rows(Qn, qsrc, (b + 1) * 64, 64, Lq);
+        stage_rows(Qn + ATC_BLK_BYTES, gsrc, (b + 1) * 64, 64, Lq);
       }
       cp_async_commit();
       if (wact) {                                        // rows of idle warps feed only dK/dV rows that are never stored

@@ -163,6 +163,18 @@ int fcmf_cls_ce_bwd(const void* pooled, const float* Wc, const float* probs, con
                     const float* dlogits_in, float row_scale, float* dlogits_ws, void* dpooled, float* dWc,
                     float* dbc, int64_t R, int64_t H, int32_t C, const fcmf_dropout* drop, int dtype, void* stream);
 
+/* ---- wide softmax cross-entropy: the IAOG decoder's vocabulary loss (run_pretraining_fcmf.py:320-322) --------- */
+/* logits [R, V] (row stride ld elements, any 2/4-byte row alignment), labels [R] int64; rows whose label equals
+ * ignore_index (or lies outside [0, V)) contribute 0. loss_rows[r] = logsumexp(logits[r]) - logits[r, label]; lse[r] is
+ * saved for the backward pass. The caller divides the sum by the number of counted rows (CrossEntropyLoss 'mean'). */
+int fcmf_vocab_ce_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t ignore_index,
+                      float* loss_rows, float* lse, int64_t R, int64_t V, int dtype, void* stream);
+/* dlogits[r, j] = (softmax(logits[r])[j] - [j == label[r]]) * scale[0]; scale is a DEVICE scalar (upstream gradient /
+ * counted rows, so no host synchronisation is needed); dlogits may alias logits (in place). */
+int fcmf_vocab_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t ignore_index,
+                      const float* lse, const float* scale, void* dlogits, int64_t ldd, int64_t R, int64_t V,
+                      int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "fcmf_box_geometry_fwd": [_vp, _vp, _vp, C.POINTER(_f32), _vp, _vp, _i64, _i32, _i32, _vp],
     "fcmf_box_geometry_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
     "fcmf_cls_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
+    "fcmf_vocab_ce_fwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp],
+    "fcmf_vocab_ce_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp],
     "fcmf_cls_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
 }
 

@@ -106,6 +106,13 @@ class FCMFSeq2Seq(nn.Module):
         return logits if is_train else (logits, enc_attentions)
 
     @staticmethod
+    def loss(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+        """The pre-training loss of run_pretraining_fcmf.py:320-322 -- CrossEntropyLoss(ignore_index=-100) over the
+        vocabulary axis of logits [B, T, V] -- as one forward and one backward kernel (no [B, V, T] permute copy)."""
+        from .. import functional as Fn
+        return Fn.vocab_cross_entropy(logits, labels, ignore_index)
+
+    @staticmethod
     def _init_weights(module):
         if isinstance(module, nn.Linear):
             module.weight.data.normal_(mean=0.0, std=0.02)

@@ -302,3 +302,28 @@ def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tenso
     """(logits [R,C] fp32, loss scalar = row_scale * sum_r CE(logits[r], labels[r])); labels=None -> logits only.
     drop: dropout on `pooled` before the classifier (fcmf_multimodal.py:49)."""
     return _ClassifierCE.apply(pooled, wc, bc, labels, row_scale, drop)
+
+
+# ------------------------------------------------------------------------------------------------- vocabulary loss
+class _VocabCE(Function):
+    @staticmethod
+    def forward(ctx, logits: Tensor, labels: Tensor, ignore_index: int):
+        labels = labels.to(torch.int64).contiguous()
+        loss_rows, lse = ops.vocab_ce_fwd(logits, labels, ignore_index)
+        counted = (labels != ignore_index).sum().clamp_min(1).to(torch.float32)     # stays on the device: no sync
+        ctx.ignore_index = ignore_index
+        ctx.save_for_backward(logits, labels, lse, counted)
+        return loss_rows.sum() / counted
+
+    @staticmethod
+    def backward(ctx, dloss: Tensor):
+        logits, labels, lse, counted = ctx.saved_tensors
+        scale = (dloss.to(torch.float32) / counted).reshape(1).contiguous()
+        return ops.vocab_ce_bwd(logits, labels, lse, scale, ctx.ignore_index), None, None
+
+
+def vocab_cross_entropy(logits: Tensor, labels: Tensor, ignore_index: int = -100) -> Tensor:
+    """mean_{counted rows} CE(logits[r], labels[r]) over a wide class axis -- nn.CrossEntropyLoss(ignore_index) of the
+    IAOG pre-training loop (run_pretraining_fcmf.py:320-322). logits [..., V] (any leading dims), labels [...]."""
+    V = logits.shape[-1]
+    return _VocabCE.apply(logits.reshape(-1, V), labels.reshape(-1), ignore_index)

@@ -273,3 +273,26 @@ def test_classifier_cross_entropy(dtype):
     p3 = pooled.detach().float().clone().requires_grad_(True)
     torch.nn.functional.cross_entropy(p3 @ wc.detach().t() + bc.detach(), labels).backward()
     assert rel_err(p2.grad, p3.grad) < TOL[dtype]
+
+
+# ------------------------------------------------------------------------------------------- vocabulary softmax-CE
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("R,V", [(37, 1002), (8, 250002), (5, 7)])
+def test_vocab_cross_entropy_matches_torch(dtype, R, V):
+    """The IAOG loss (CrossEntropyLoss(ignore_index=-100) over the 250 002-entry vocabulary): rows start at odd
+    alignments (V % 8 == 2), some rows are ignored, gradients flow through the mean over the counted rows."""
+    logits = (rnd(R, V, dtype=dtype, scale=3.0)).requires_grad_(True)
+    labels = torch.randint(0, V, (R,), device=dev())
+    labels[1::4] = -100
+    loss = Fn.vocab_cross_entropy(logits, labels)
+    ref_in = logits.detach().float().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, ignore_index=-100)
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    (loss * 1.7).backward()
+    (ref * 1.7).backward()
+    assert rel_err(logits.grad, ref_in.grad) < TOL[dtype]
+    assert float(logits.grad[1].abs().max()) == 0.0                   # an ignored row gets no gradient
+    # 3-D call as the training loop makes it ([B, T, V] logits, [B, T] labels)
+    if R % 2 == 0:
+        l3 = Fn.vocab_cross_entropy(logits.detach().view(2, R // 2, V), labels.view(2, R // 2))
+        assert abs(l3.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))

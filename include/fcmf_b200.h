@@ -82,10 +82,12 @@ int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_idx, const fl
                 int dtype, void* stream);
 /* ds = dLN/ds . (dy + dy_add)  (same shape as x; dy_add may be NULL: the second gradient stream of a
  * residual fan-out); dgamma/dbeta[H] accumulate (+=) in fp32. With dropout, ds is the gradient of the residual
- * and dx (required then, ignored otherwise) = keep * ds / (1-p) is the gradient of x. */
+ * and dx (required then, ignored otherwise) = keep * ds / (1-p) is the gradient of x.
+ * dy_every > 0: dy is compact [ceil(M / dy_every), H] and holds the gradient of rows 0, dy_every, 2*dy_every, ... only; every
+ * other row's upstream gradient is zero (BertPooler keeps token 0 of each per-image branch, mm_modeling.py:428). 0 = dense. */
 int fcmf_ln_bwd(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* res_idx, const float* gamma,
                 const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta,
-                int64_t M, int64_t H, const fcmf_dropout* drop, int dtype, void* stream);
+                int64_t M, int64_t H, const fcmf_dropout* drop, int64_t dy_every, int dtype, void* stream);
 
 /* add[b, j] = (1 - mask[b, j]) * -10000 for j < n   (fcmf_pretraining.py:53-56, 97-100, 133-136) */
 int fcmf_mask_additive(const int64_t* mask, int64_t ldmask, float* add, int64_t rows, int64_t n, void* stream);

@@ -43,7 +43,7 @@ PROTOTYPES = {
     "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "fcmf_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.POINTER(Dropout), C.c_int, _vp],
-    "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(Dropout), C.c_int, _vp],
+    "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(Dropout), _i64, C.c_int, _vp],
     "fcmf_mask_additive": [_vp, _i64, _vp, _i64, _i64, _vp],
     "fcmf_gather_sum_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp],
     "fcmf_dtanh": [_vp, _vp, _vp, _i64, C.c_int, _vp],

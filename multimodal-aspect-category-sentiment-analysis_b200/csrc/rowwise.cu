@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 4)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* __restrict__ x, const T* __restrict__ res,
               const int32_t* __restrict__ res_idx, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds, T* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H, fcmf_dropout drop) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int H, fcmf_dropout drop, int dy_every) {
   constexpr int N = Vec16<T>::N;
   extern __shared__ float red[];                      // [LN_WARPS][2][H] column partial sums | gamma[H]
   float* gsm = red + (size_t)LN_WARPS * 2 * H;
@@ -117,7 +117,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += stride) {
     const T* xr = x + row * H;
     const T* rr = res ? res + (int64_t)(res_idx ? res_idx[row] : row) * H : nullptr;
-    const T* dyr = dy + row * H;
+    // dy_every > 0: dy is COMPACT -- only rows m with m % dy_every == 0 have a gradient (row m / dy_every of dy), the others
+    // are structurally zero (BertPooler reads token 0 of every per-image branch, mm_modeling.py:428): no zero tensor is
+    // materialised and nothing is read for them
+    const bool has_dy = dy_every <= 0 || (row % dy_every) == 0;
+    const T* dyr = dy + (dy_every > 0 ? row / dy_every : row) * H;
     const float mu = mean[row], rs = rstd[row];
     float xh[VPL][N], gy[VPL][N];
     float s1 = 0.f, s2 = 0.f;
@@ -129,7 +133,12 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
       const int c = (i * 32 + lane) * N;
       keep[i] = 0xffffffffu;
       if (c < H) {
-        Vec16<T> a, d; a.load(xr + c); d.load(dyr + c);
+        Vec16<T> a, d; a.load(xr + c);
+        if (has_dy) d.load(dyr + c);
+        else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) d.v[j] = 0.f;
+        }
         if (DROP) {
           uint32_t kb = 0;
 #pragma unroll
@@ -227,18 +236,18 @@ static int ln_fwd_launch(const void* x, const void* res, const int32_t* idx, con
 template <typename T, int VPL>
 static int ln_bwd_launch(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* idx, const float* gamma,
                          const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta, int64_t M, int H,
-                         const fcmf_dropout* drop, cudaStream_t st) {
+                         const fcmf_dropout* drop, int dy_every, cudaStream_t st) {
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   const size_t smem = sizeof(float) * (LN_WARPS * 2 + 1) * H;
   if (drop_on(drop))
     ln_bwd_kernel<T, VPL, true><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
-        (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, (T*)dx, dgamma, dbeta, M, H, *drop);
+        (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, (T*)dx, dgamma, dbeta, M, H, *drop, dy_every);
   else
     ln_bwd_kernel<T, VPL, false><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(
         (const T*)dy, (const T*)dy_add, (const T*)x, (const T*)res, idx, gamma, mean, rstd, (T*)ds, (T*)dx, dgamma, dbeta, M, H,
-        drop_or_off(nullptr));
+        drop_or_off(nullptr), dy_every);
   FCMF_LAUNCH_OK();
   return 0;
 }
@@ -360,17 +369,18 @@ extern "C" int fcmf_ln_fwd(const void* x, const void* res, const int32_t* res_id
 
 extern "C" int fcmf_ln_bwd(const void* dy, const void* dy_add, const void* x, const void* res, const int32_t* res_idx, const float* gamma,
                            const float* mean, const float* rstd, void* ds, void* dx, float* dgamma, float* dbeta, int64_t M,
-                           int64_t H64, const fcmf_dropout* drop, int dtype, void* stream) {
+                           int64_t H64, const fcmf_dropout* drop, int64_t dy_every, int dtype, void* stream) {
   const int H = (int)H64;
   FCMF_CHECK_ARG(M >= 0 && H > 0, "ln_bwd: bad shape");
   FCMF_CHECK_ARG(H % (dtype == FCMF_BF16 ? 8 : 4) == 0, "ln_bwd: H=%d must be a multiple of the 16-byte vector", H);
   FCMF_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(ds) && (!res || aligned16(res)) && (!dy_add || aligned16(dy_add)), "ln_bwd: alignment");
   FCMF_CHECK_ARG(drop_check(drop) == 0, "ln_bwd: dropout p must be in [0, 1)");
   FCMF_CHECK_ARG(!drop_on(drop) || (dx && aligned16(dx)), "ln_bwd: dropout needs the second output dx (16-byte aligned)");
+  FCMF_CHECK_ARG(dy_every >= 0 && dy_every < (1LL << 31), "ln_bwd: bad dy_every");
   if (M == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, st);
-  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, st);
+  if (dtype == FCMF_BF16) FCMF_LN_DISPATCH(bf16, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, (int)dy_every, st);
+  if (dtype == FCMF_F32) FCMF_LN_DISPATCH(float, ln_bwd_launch, dy, dy_add, x, res, res_idx, gamma, mean, rstd, ds, dx, dgamma, dbeta, M, H, drop, (int)dy_every, st);
   return fail(FCMF_ERR_ARG, "ln_bwd: bad dtype %d", dtype);
 }
 

@@ -98,15 +98,18 @@ class _LayerTail(Function):
 
     @staticmethod
     def forward(ctx, a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor],
-                wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2, engine: int, drop1: Optional[ops.Drop], drop2: Optional[ops.Drop]):
+                wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2, engine: int, drop1: Optional[ops.Drop], drop2: Optional[ops.Drop],
+                out_every: int):
         dt = a.dtype
         d = ops.gemm_tn(a, ops.cast_matrix(wo, dt), bo, EPI_NONE, engine=engine)
         x1, mean1, rstd1 = ops.ln_fwd(d, res_src, res_idx, g1, b1, drop=drop1)      # LN(dropout(dense) + residual)
         g, pre = ops.gemm_tn(x1, ops.cast_matrix(w1, dt), bi1, EPI_GELU, engine=engine, want_aux=True)
         o = ops.gemm_tn(g, ops.cast_matrix(w2, dt), bi2, EPI_NONE, engine=engine)
         y, mean2, rstd2 = ops.ln_fwd(o, x1, None, g2, b2, drop=drop2)
-        ctx.engine, ctx.drop1, ctx.drop2 = engine, drop1, drop2
+        ctx.engine, ctx.drop1, ctx.drop2, ctx.out_every = engine, drop1, drop2, out_every
         ctx.save_for_backward(a, res_src, res_idx, res_inv, wo, g1, w1, w2, g2, d, x1, pre, g, o, mean1, rstd1, mean2, rstd2)
+        if out_every > 1:            # the caller consumes rows 0, out_every, ... only (token 0 of every problem): hand out that view
+            return y.view(y.shape[0] // out_every, out_every, y.shape[1])[:, 0, :]
         return y
 
     @staticmethod
@@ -114,8 +117,10 @@ class _LayerTail(Function):
         (a, res_src, res_idx, res_inv, wo, g1, w1, w2, g2, d, x1, pre, g, o, mean1, rstd1, mean2, rstd2) = ctx.saved_tensors
         eng, dt = ctx.engine, a.dtype
         dy = dy.contiguous()
-        # ds2 = grad of s2 = dropout(o) + x1 (goes to x1), do2 = grad of o (== ds2 without dropout)
-        ds2, do2, dg2, db2 = ops.ln_bwd_drop(dy, None, o, x1, None, g2, mean2, rstd2, ctx.drop2)
+        # ds2 = grad of s2 = dropout(o) + x1 (goes to x1), do2 = grad of o (== ds2 without dropout); with out_every the
+        # incoming gradient is compact (one row per problem) and the zero rows are never materialised
+        ds2, do2, dg2, db2 = ops.ln_bwd_drop(dy, None, o, x1, None, g2, mean2, rstd2, ctx.drop2,
+                                             dy_every=ctx.out_every if ctx.out_every > 1 else 0)
         dw2, dbi2 = ops.gemm_wgrad(do2, g, engine=eng)
         dpre = ops.gemm_tn(do2, ops.cast_matrix(w2, dt, transpose=True), None, EPI_DGELU, aux=pre, engine=eng)
         dw1, dbi1 = ops.gemm_wgrad(dpre, x1, engine=eng)
@@ -130,16 +135,19 @@ class _LayerTail(Function):
                 dres = ds1
             else:
                 dres = ops.gather_sum_rows(ds1, res_inv, res_src.shape[0], res_inv.shape[1])
-        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None, None, None
+        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None, None, None, None
 
 
 def layer_tail(a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor], params: Sequence[Tensor],
-               engine: int = ENGINE_AUTO, drop1: Optional[ops.Drop] = None, drop2: Optional[ops.Drop] = None) -> Tensor:
+               engine: int = ENGINE_AUTO, drop1: Optional[ops.Drop] = None, drop2: Optional[ops.Drop] = None,
+               out_every: int = 0) -> Tensor:
     """params = (Wo, bo, ln1.w, ln1.b, W1, b1, W2, b2, ln2.w, ln2.b). Row m of `a` takes residual row
     res_idx[m] of res_src (identity when res_idx is None); res_inv [rows(res_src), G] lists, for every residual
     row, the rows of `a` that used it (-1 padded) so that the backward reduction needs no atomics.
-    drop1 / drop2: hidden dropout of BertSelfOutput / BertOutput (mm_modeling.py:278, 326), mask row = row of `a`."""
-    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine, drop1, drop2)
+    drop1 / drop2: hidden dropout of BertSelfOutput / BertOutput (mm_modeling.py:278, 326), mask row = row of `a`.
+    out_every > 1: every row is computed, but only rows 0, out_every, 2*out_every, ... are returned ([rows/out_every, H], a
+    view) -- what BertPooler reads of a per-image branch; the backward pass then takes a compact gradient."""
+    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine, drop1, drop2, out_every)
 
 
 # ------------------------------------------------------------------------------------------------- attention

@@ -185,9 +185,10 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     plan1 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("t2i_attn", t2i.attention.self)).add("q", 0, 0, Lq, ix.p2ba, ix.ba2p) \
         .add("k", 1, 0, P, ix.p2bi, ix.bi2p).add("v", 1, H, P, ix.p2bi, ix.bi2p)
     ctx1 = Fn.folded_attention(plan1, (q_t, kv_p), mask_add, None)                                      # [NP*Lq, H]
+    # every row is computed (rows="full"), but BertPooler reads token 0 only: the tail hands out that row of each problem
     y1 = Fn.layer_tail(ctx1, seq2, ix.t2i_res_idx, ix.t2i_res_inv, _tail_params(t2i), engine=engine,
-                       drop1=drop("t2i_out1", t2i.attention.output), drop2=drop("t2i_out2", t2i.output))
-    h_img = Fn.linear(y1.view(NP, Lq, H)[:, 0, :], enc.text2img_pooler.dense.weight, enc.text2img_pooler.dense.bias,
+                       drop1=drop("t2i_out1", t2i.attention.output), drop2=drop("t2i_out2", t2i.output), out_every=Lq)
+    h_img = Fn.linear(y1, enc.text2img_pooler.dense.weight, enc.text2img_pooler.dense.bias,
                       act="tanh", engine=engine)                                                        # [NP, H]
 
     # ---- text + ROI branch ---------------------------------------------------------------------------------
@@ -198,7 +199,6 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
         ctx2 = Fn.folded_attention(plan2, (q0_mm, kv_t, kv_r), mask_add, None)                          # [NP, H]
         y2 = Fn.layer_tail(ctx2, seq2, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine,
                            drop1=drop("mm_out1", mm.attention.output), drop2=drop("mm_out2", mm.output))
-        Sq = 1
     else:
         plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("mm_attn", mm.attention.self))
         for role, col in (("q", 0), ("k", H), ("v", 2 * H)):
@@ -206,9 +206,8 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
         ctx2 = Fn.folded_attention(plan2, (qkv_t, qkv_r), mask_add, None)                               # [NP*S, H]
         text_roi = torch.cat((seq2, rel), 0)                                                            # residual rows
         y2 = Fn.layer_tail(ctx2, text_roi, ix.roi_res_idx, ix.roi_res_inv, _tail_params(mm), engine=engine,
-                           drop1=drop("mm_out1", mm.attention.output), drop2=drop("mm_out2", mm.output))
-        Sq = S
-    r_img = Fn.linear(y2.view(NP, Sq, H)[:, 0, :], enc.text2roi_pooler.dense.weight, enc.text2roi_pooler.dense.bias,
+                           drop1=drop("mm_out1", mm.attention.output), drop2=drop("mm_out2", mm.output), out_every=S)
+    r_img = Fn.linear(y2, enc.text2roi_pooler.dense.weight, enc.text2roi_pooler.dense.bias,
                       act="tanh", engine=engine)                                                        # [NP, H]
 
     # ---- fusion layer: [CLS] + h_1..NI + r_1..NI (fcmf_pretraining.py:127-139), same mm_attention weights ----

@@ -296,3 +296,19 @@ def test_vocab_cross_entropy_matches_torch(dtype, R, V):
     if R % 2 == 0:
         l3 = Fn.vocab_cross_entropy(logits.detach().view(2, R // 2, V), labels.view(2, R // 2))
         assert abs(l3.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_layernorm_bwd_compact_upstream_gradient(dtype):
+    """dy_every: only rows 0, E, 2E, ... carry an upstream gradient (BertPooler keeps token 0 of each problem); the kernel
+    takes the compact [M/E, H] gradient and must equal the dense call with zeros in the other rows."""
+    M, H, E = 6 * 29, 768, 29
+    x, res = rnd(M, H, dtype=dtype), rnd(M, H, dtype=dtype, seed=2)
+    w, b = (1 + 0.1 * rnd(H, seed=4)), 0.1 * rnd(H, seed=5)
+    _, mean, rstd = ops.ln_fwd(x, res, None, w, b)
+    dyc = rnd(M // E, H, dtype=dtype, seed=7)
+    dense = torch.zeros(M, H, dtype=dtype, device=dev())
+    dense[::E] = dyc
+    ds0, _, dg0, db0 = ops.ln_bwd_drop(dense, None, x, res, None, w, mean, rstd)
+    ds1, _, dg1, db1 = ops.ln_bwd_drop(dyc, None, x, res, None, w, mean, rstd, dy_every=E)
+    assert torch.equal(ds0, ds1) and rel_err(dg1, dg0) < 1e-5 and rel_err(db1, db0) < 1e-5

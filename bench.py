@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--mode", default=os.environ.get("FCMF_BENCH_MODE", "train"), choices=["train", "eval"],
                     help="train: every nn.Dropout of the reference path applied in-kernel (p=0.1); eval: dropout off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=float(os.environ.get("FCMF_BENCH_MAX_SECONDS", "1800")),
+                    help="watchdog: a run that has not finished by then exits with code 3 instead of hanging the box")
     ap.add_argument("--no-second-mode", action="store_true")
     return ap.parse_args()
 
@@ -167,15 +169,43 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(base, "exec"), "rows": "exec (everything the reference executes)",
-                   "sample_batch": b},
+                   "sample_batch": b, "mode": "dropout off (the oracle port's deterministic path; the reference's own "
+                                             "train() step would add its nn.Dropout work on top)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
 
+def leave(world, dist, torch):
+    """End of a multi-rank run. One 2-GPU run of this script printed its JSON line and then never exited: the teardown of
+    the NCCL communicator (whose collectives are also captured inside a live CUDA graph) blocked. The measurement is over
+    at this point, so: a last barrier (nobody is still inside a collective that reads a peer's memory), flush, and leave
+    without running the communicator / graph destructors."""
+    if world <= 1:
+        return
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------ our arm
+def start_watchdog(seconds: float) -> None:
+    def bark():
+        sys.stderr.write(f"bench.py: watchdog: not finished after {seconds:.0f} s, exiting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    if seconds > 0:
+        t = threading.Timer(seconds, bark)
+        t.daemon = True
+        t.start()
+
+
 def main():
     args = parse()
+    start_watchdog(args.max_seconds)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -344,6 +374,15 @@ def main():
     e2e = {"value": n_gpus * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e}
 
+    # ---- the other dropout mode beside the headline (same rows, same protocol) -------------------------------------
+    other_mode = None
+    if not args.no_second_mode:
+        model.eval() if args.mode == "train" else model.train()
+        ms_m, l_m = timed(lambda: step(res, args.rows), max(3, min(args.steps, 10)), 3)
+        other_mode = {"mode": "eval" if args.mode == "train" else "train", "rows": args.rows,
+                      "value": n_gpus * B / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m, "gpu_launches": l_m}
+        model.train() if args.mode == "train" else model.eval()
+
     # ---- the other row mode beside the headline (both must be shown, each labelled) -------
     other = None
     if not args.no_second_mode:
@@ -363,18 +402,8 @@ def main():
             except Exception as e:                                   # capture is an optimisation, never a requirement
                 other["graph_replay"] = {"unavailable": repr(e)[:300]}
 
-    # ---- the other dropout mode beside the headline (same rows, same protocol) -------------------------------------
-    other_mode = None
-    if not args.no_second_mode:
-        model.eval() if args.mode == "train" else model.train()
-        ms_m, l_m = timed(lambda: step(res, args.rows), max(3, min(args.steps, 10)), 3)
-        other_mode = {"mode": "eval" if args.mode == "train" else "train", "rows": args.rows,
-                      "value": n_gpus * B / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m, "gpu_launches": l_m}
-        model.train() if args.mode == "train" else model.eval()
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave(world, dist, torch)
         return
 
     cpu = None
@@ -401,8 +430,7 @@ def main():
         "executed_tflops": {"gemm_only": g_flops / max(args.steps, 1) / (ms * 1e-3) / 1e12},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave(world, dist, torch)
 
 
 if __name__ == "__main__":

@@ -52,3 +52,34 @@ def test_loss_is_sum_of_per_aspect_means():
     want = sum(torch.nn.functional.cross_entropy(logits[:, a], labels[:, a]) for a in range(2))
     folded = torch.nn.functional.cross_entropy(logits.reshape(-1, 4), labels.reshape(-1), reduction="sum") / 3
     assert torch.allclose(want, folded, atol=1e-6)
+
+
+def test_oracle_dropout_plan_is_identity_at_p0_and_deterministic():
+    """train()-mode oracle (DropPlan): p = 0 reproduces the eval path bit for bit, a seed reproduces its masks, masks of
+    different sites / seeds differ, and every site's keep rate is the requested one."""
+    import numpy as np
+    from oracle import dropout_mask as DM
+    from _util import pkg, synth
+    sites = pkg("fusion").DROP_SITES
+    dims = synth.FusionDims(batch=2, aspects=2, seq_len=12, num_imgs=2, num_roi=3)
+    params = synth.make_params(dims, seed=3)
+    batch = synth.make_batch(dims, seed=4, mask="bernoulli")
+
+    def run(plan):
+        with torch.no_grad():
+            return O.aspect_loop(batch["sequence_output"], batch["visual_embeds_att"], batch["roi_embeds_att"],
+                                 batch["roi_coors"], batch["added_attention_mask"], batch["labels"], params, dims.heads,
+                                 dims.num_imgs, dims.num_roi, drop=plan)[0]
+    base = run(None)
+    assert torch.equal(run(O.DropPlan(1, sites, 2, 2, 2, 0.0)), base)
+    a, b, c = run(O.DropPlan(7, sites, 2, 2, 2, 0.1)), run(O.DropPlan(7, sites, 2, 2, 2, 0.1)), run(O.DropPlan(8, sites, 2, 2, 2, 0.1))
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, base)
+    only_head = run(O.DropPlan(7, sites, 2, 2, 2, {"head": 0.5}))
+    assert not torch.equal(only_head, base)
+    assert len(set(sites.values())) == len(sites)                    # one seed per nn.Dropout site
+    for site in sites.values():
+        m = DM.keep_mask(DM.site_seed(7, site), np.arange(2048), 256, 0.1)
+        assert abs(m.mean() - 0.9) < 3e-3
+    m1 = DM.keep_mask(DM.site_seed(7, 1), np.arange(256), 256, 0.1)
+    m2 = DM.keep_mask(DM.site_seed(7, 2), np.arange(256), 256, 0.1)
+    assert (m1 != m2).mean() > 0.1

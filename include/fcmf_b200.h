@@ -52,6 +52,10 @@ typedef struct {
 int fcmf_dropout_keep(float p, uint64_t seed, uint64_t row, uint32_t col);
 
 int fcmf_abi_version(void);
+/* sizeof / offsetof audit of the by-value structs (0 sizeof(fcmf_dropout), 1 .seed, 2 .seed_dev, 3 sizeof(fcmf_seg), 4 .idx,
+ * 5 sizeof(fcmf_attn_desc), 6 .mask_add, 7 .bias, 8 .scale, 9 .causal, 10 .drop; -1 otherwise): lets a binding check its
+ * mirror of the layouts against the compiled library. */
+int fcmf_abi_layout(int which);
 const char* fcmf_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long fcmf_kernel_launches(void);

@@ -38,6 +38,7 @@ class AttnDesc(C.Structure):
 # name -> argtypes (every entry point returns int); must list EVERY symbol include/fcmf_b200.h declares.
 PROTOTYPES = {
     "fcmf_abi_version": [],
+    "fcmf_abi_layout": [C.c_int],
     "fcmf_dropout_keep": [_f32, C.c_uint64, C.c_uint64, C.c_uint32],
     "fcmf_device_info": [C.POINTER(C.c_int)] * 3,
     "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],

@@ -1,6 +1,7 @@
 // Error plumbing, device queries and the ABI version entry points.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stddef.h>
 #include <atomic>
 #include <mutex>
 
@@ -60,4 +61,23 @@ extern "C" int fcmf_device_info(int* sm, int* major, int* minor) {
 extern "C" int fcmf_dropout_keep(float p, uint64_t seed, uint64_t row, uint32_t col) {
   const uint32_t thr = fcmf::drop_threshold(p);
   return fcmf::drop_keep(fcmf::drop_rowseed(seed, row), col, thr) ? 1 : 0;
+}
+
+// Layout audit for foreign-function bindings: sizeof / field offsets of the by-value structs of the ABI, so that a ctypes /
+// cgo / JNI mirror can be checked against the compiled library without a GPU (tests/test_cpu_host.py does).
+extern "C" int fcmf_abi_layout(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(fcmf_dropout);
+    case 1: return (int)offsetof(fcmf_dropout, seed);
+    case 2: return (int)offsetof(fcmf_dropout, seed_dev);
+    case 3: return (int)sizeof(fcmf_seg);
+    case 4: return (int)offsetof(fcmf_seg, idx);
+    case 5: return (int)sizeof(fcmf_attn_desc);
+    case 6: return (int)offsetof(fcmf_attn_desc, mask_add);
+    case 7: return (int)offsetof(fcmf_attn_desc, bias);
+    case 8: return (int)offsetof(fcmf_attn_desc, scale);
+    case 9: return (int)offsetof(fcmf_attn_desc, causal);
+    case 10: return (int)offsetof(fcmf_attn_desc, drop);
+    default: return -1;
+  }
 }

@@ -95,3 +95,50 @@ def test_dropout_mask_restatement_matches_the_library():
     assert abs(np.corrcoef(big[:-1].ravel(), big[1:].ravel())[0, 1]) < 5e-3              # adjacent rows
     thr, inv = DM.threshold(0.1)
     assert thr == 6554 and abs(inv - 1.0 / (1.0 - 6554 / 65536)) < 1e-6
+
+
+def test_ctypes_struct_layouts_match_the_compiled_library():
+    """The by-value structs of the ABI (fcmf_dropout, fcmf_seg, fcmf_attn_desc) as mirrored in _lib.py have the sizes and
+    field offsets the compiled library uses (a silent mismatch would corrupt every attention launch)."""
+    L = pkg("_lib")
+    lib = L.load()
+    want = [ctypes.sizeof(L.Dropout), L.Dropout.seed.offset, L.Dropout.seed_dev.offset, ctypes.sizeof(L.Seg), L.Seg.idx.offset,
+            ctypes.sizeof(L.AttnDesc), L.AttnDesc.mask_add.offset, L.AttnDesc.bias.offset, L.AttnDesc.scale.offset,
+            L.AttnDesc.causal.offset, L.AttnDesc.drop.offset]
+    got = [lib.fcmf_abi_layout(i) for i in range(len(want))]
+    assert got == want, (got, want)
+    assert lib.fcmf_abi_layout(99) == -1
+
+
+def test_attention_gradient_row_tables():
+    """functional._identity_rows / _group_rows: the per-problem gradient rows that gather_sum_rows reduces into the rows of
+    a shared tensor (text rows shared by the images of a (sample, aspect); patch / ROI rows shared by the aspects)."""
+    Fn = pkg("functional")
+    dev = torch.device("cpu")
+    NP, L, off, rows = 6, 5, 2, 3
+    ident = Fn._identity_rows(NP, L, off, rows, dev)
+    assert ident.shape == (NP * rows, 1)
+    assert ident.view(NP, rows).tolist() == [[p * L + off + r for r in range(rows)] for p in range(NP)]
+    inv = torch.tensor([[0, 2, -1], [1, 3, 5]], dtype=torch.int32)              # 2 groups, problems of each (-1 padded)
+    grp = Fn._group_rows(inv, L, off, rows)
+    assert grp.shape == (2 * rows, 3)
+    for g in range(2):
+        for r in range(rows):
+            want = [(-1 if p < 0 else p * L + off + r) for p in inv[g].tolist()]
+            assert grp[g * rows + r].tolist() == want
+
+
+def test_dropout_site_seeds_and_plan_objects():
+    Fn, ops, fusion = pkg("functional"), pkg("ops"), pkg("fusion")
+    from oracle import dropout_mask as DM
+    assert Fn.site_drop(None, 3, 0.1) is None and Fn.site_drop(5, 3, 0.0) is None          # eval / p = 0: no Drop object
+    d = Fn.site_drop(5, fusion.DROP_SITES["mm_attn"], 0.1)
+    assert isinstance(d, ops.Drop) and d.seed == DM.site_seed(5, fusion.DROP_SITES["mm_attn"]) and d.struct().p == pytest.approx(0.1)
+    torch.manual_seed(1)
+    a = Fn.new_step_seed()
+    torch.manual_seed(1)
+    assert Fn.new_step_seed() == a and 0 <= a < 2 ** 62
+    with pytest.raises(ValueError):
+        ops.Drop(1.0, 1)
+    plan = Fn.AttnPlan(4, 2, 64, drop=d).add("q", 0, 0, 7, None, None).add("k", 0, 128, 7, None, None).add("k", 1, 0, 3, None, None)
+    assert plan.Lq == 7 and plan.Lk == 10 and plan.drop is d

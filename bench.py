@@ -137,6 +137,38 @@ def cpu_baseline(torch, synth, base_dims, budget_s=20.0):
                       f"batch {b} of the same shapes, {n} timed steps after 1 warm-up, {dt:.2f} s/step"}
 
 
+def eager_device_baseline(torch, synth, dims, dev, steps=2):
+    """The honest on-box bar: the reference's algorithm exactly as its PyTorch code executes it --
+    per-aspect, per-image loops of stock torch ops (oracle port, test infrastructure) -- run eagerly ON THE SAME GPU, fp32 and
+    bf16 autocast, same batch, dropout off. Reported beside the kernel path; never part of the measured step."""
+    from oracle import fcmf_oracle as O
+    pkg = importlib.import_module(PKG)
+    params = {k: v.to(dev).requires_grad_(True) for k, v in pkg.synth.make_params(dims, seed=42).items()}
+    batch = {k: v.to(dev) for k, v in pkg.synth.make_batch(dims, seed=1234).items()}
+    seq = batch["sequence_output"].requires_grad_(True)
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+    out = {"unit": UNIT, "batch": dims.batch, "what": "oracle port of the reference's eager PyTorch path on this device"}
+    for name, amp in (("fp32", False), ("bf16_autocast", True)):
+        def step():
+            for p in params.values():
+                p.grad = None
+            seq.grad = None
+            with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=amp):
+                _, loss = O.aspect_loop(seq, batch["visual_embeds_att"], batch["roi_embeds_att"], batch["roi_coors"],
+                                        batch["added_attention_mask"], batch["labels"], params, dims.heads, dims.num_imgs,
+                                        dims.num_roi)
+            loss.backward()
+        step()
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        sync()
+        dt = (time.perf_counter() - t0) / steps
+        out[name] = {"value": dims.batch / dt, "ms_per_step": dt * 1e3}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this workload (oracle port; /root/reference is a Python
     package that cannot travel to the GPU box), all host threads, a bounded sample per step."""
@@ -413,6 +445,17 @@ def main():
         except Exception as e:                                   # the CPU leg must never take the GPU number down
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
+    eager = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()                                 # hand the measured path's cached blocks back first
+        for b_try in (dims.batch, 16, 4):                        # the eager path keeps every intermediate alive for backward
+            try:
+                eager = eager_device_baseline(torch, synth, synth.FusionDims(**{**dims.to_dict(), "batch": b_try}), dev)
+                break
+            except Exception as e:                               # a baseline must never take the measurement down
+                eager = {"unavailable": repr(e)[:200]}
+                torch.cuda.empty_cache()
+
     fl = {m: synth.flops_forward_per_sample(dims, m) * 3 for m in ("exec", "full", "live")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -425,7 +468,7 @@ def main():
                    "step": "fusion forward + backward" + (" + bucketed NCCL gradient all-reduce overlapped with backward" if n_gpus > 1 else "")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step), "roofline": roofline, "cpu_baseline": cpu,
-        "other_row_mode": other, "other_dropout_mode": other_mode,
+        "other_row_mode": other, "other_dropout_mode": other_mode, "reference_eager_gpu": eager,
         "flops_fwd_bwd_per_sample": fl,
         "executed_tflops": {"gemm_only": g_flops / max(args.steps, 1) / (ms * 1e-3) / 1e12},
     }

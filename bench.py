@@ -448,7 +448,8 @@ def main():
     eager = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()                                 # hand the measured path's cached blocks back first
-        for b_try in (dims.batch, 16, 4):                        # the eager path keeps every intermediate alive for backward
+        for b_try in (16, 4):                                    # the eager path keeps every intermediate of all 6 x 7 passes
+                                                                 # alive for backward (~1.6 GB per sample in fp32): bounded batch
             try:
                 eager = eager_device_baseline(torch, synth, synth.FusionDims(**{**dims.to_dict(), "batch": b_try}), dev)
                 break

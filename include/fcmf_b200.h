@@ -76,6 +76,12 @@ int fcmf_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const f
 int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, float* db,
                     int64_t M, int64_t N, int64_t K, int accumulate, int dtype, int engine, void* stream);
 
+/* Planning query (host only, launches nothing): tiling of the tcgen05 weight-gradient GEMM for this shape -- cta_pairs = 1
+ * when the CTA-pair kernel is used, tiles = 256x256 (or 128xBN) output tiles, splits = split-K factor, workers = CTA pairs (or
+ * CTAs) that walk the tiles*splits work units in waves. Wave efficiency = units / (ceil(units / workers) * workers). */
+int fcmf_gemm_wgrad_plan(int64_t M, int64_t N, int64_t K, int32_t* cta_pairs, int32_t* tiles, int32_t* splits,
+                         int32_t* workers);
+
 /* ---- row-wise kernels ------------------------------------------------------------------------------ */
 /* y[m,:] = gamma * (s - mean)/sqrt(var + eps) + beta with s = x[m,:] + res[res_idx ? res_idx[m] : m, :]
  * (res may be NULL).  TF-style LayerNorm: biased variance, eps inside the sqrt (mm_modeling.py:166-171),

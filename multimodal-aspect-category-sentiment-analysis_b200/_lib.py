@@ -43,6 +43,7 @@ PROTOTYPES = {
     "fcmf_device_info": [C.POINTER(C.c_int)] * 3,
     "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "fcmf_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "fcmf_gemm_wgrad_plan": [_i64, _i64, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],
     "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.POINTER(Dropout), C.c_int, _vp],
     "fcmf_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(Dropout), _i64, C.c_int, _vp],
     "fcmf_mask_additive": [_vp, _i64, _vp, _i64, _i64, _vp],

@@ -240,3 +240,13 @@ extern "C" int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int6
     return gemm_tc_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, st);
   return gemm_simt_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, dtype, st);
 }
+
+// Host-only planning query: how the tcgen05 weight-gradient GEMM would tile and split this shape (no launch, no GPU needed).
+extern "C" int fcmf_gemm_wgrad_plan(int64_t M, int64_t N, int64_t K, int32_t* cta_pairs, int32_t* tiles, int32_t* splits,
+                                    int32_t* workers) {
+  FCMF_CHECK_ARG(M > 0 && N > 0 && K > 0 && cta_pairs && tiles && splits && workers, "gemm_wgrad_plan: bad arguments");
+  int p = 0, t = 0, s = 0, w = 0;
+  gemm_tc_wgrad_plan(M, N, K, &p, &t, &s, &w);
+  *cta_pairs = p; *tiles = t; *splits = s; *workers = w;
+  return 0;
+}

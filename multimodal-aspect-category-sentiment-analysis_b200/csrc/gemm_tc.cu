@@ -809,4 +809,19 @@ int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, floa
   return bn == 256 ? launch<256, true, true>(m, P, st) : launch<128, true, true>(m, P, st);
 }
 
+// Tiling decision of gemm_tc_wgrad for a shape, without launching anything (host only): lets callers and the CPU
+// test-suite audit the wave efficiency of the split-K choice. workers = CTA pairs (2-CTA kernel) or CTAs.
+void gemm_tc_wgrad_plan(int64_t M, int64_t N, int64_t K, int* pair, int* tiles, int* splits, int* workers) {
+  const int k_blocks = (int)((M + TC_BK - 1) / TC_BK);
+  const bool two = use_2cta() && N % 256 == 0 && K % 256 == 0;
+  int t, w;
+  if (two) { t = (int)(N / 256) * (int)(K / 256); w = sm_count() / 2; }
+  else {
+    const int bn = (K % 256 == 0) ? 256 : 128;
+    t = (int)((N + TC_BM - 1) / TC_BM) * (int)((K + bn - 1) / bn);
+    w = sm_count();
+  }
+  *pair = two ? 1 : 0; *tiles = t; *workers = w; *splits = pick_splits(t, w, k_blocks);
+}
+
 }  // namespace fcmf

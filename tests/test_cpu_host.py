@@ -142,3 +142,39 @@ def test_dropout_site_seeds_and_plan_objects():
         ops.Drop(1.0, 1)
     plan = Fn.AttnPlan(4, 2, 64, drop=d).add("q", 0, 0, 7, None, None).add("k", 0, 128, 7, None, None).add("k", 1, 0, 3, None, None)
     assert plan.Lq == 7 and plan.Lk == 10 and plan.drop is d
+
+
+def test_weight_gradient_split_k_fills_the_last_wave():
+    """The split-K factor of the tcgen05 weight-gradient GEMM is chosen for the fill of the LAST wave of (tile, split)
+    units (round 1: ceil(workers / tiles) left 27-45 % of the kernel idle). Every weight-gradient shape of the config-2
+    step must run at >= 80 % wave efficiency. Host-only planning query: no GPU needed (148 SMs assumed without one)."""
+    lib = pkg("_lib").load()
+    i32 = ctypes.c_int32
+    shapes = [(456960, 3072, 768), (456960, 768, 3072), (456960, 768, 768), (467712, 768, 768), (65280, 2304, 768),
+              (21952, 768, 2048), (21952, 1536, 768), (65280, 768, 768), (5760, 768, 768), (1792, 2304, 768)]
+    for M, N, K in shapes:
+        pair, tiles, splits, workers = i32(), i32(), i32(), i32()
+        assert lib.fcmf_gemm_wgrad_plan(M, N, K, ctypes.byref(pair), ctypes.byref(tiles), ctypes.byref(splits), ctypes.byref(workers)) == 0
+        units = tiles.value * splits.value
+        waves = -(-units // workers.value)
+        assert 1 <= splits.value <= 32 and units / (waves * workers.value) >= 0.8, (M, N, K, tiles.value, splits.value)
+    assert lib.fcmf_gemm_wgrad_plan(0, 1, 1, None, None, None, None) != 0
+
+
+def test_gelu_tanh_fit_error_bounds():
+    """The one-MUFU GELU of the bf16 GEMM epilogues (csrc/common.cuh: gelu_erf_fast / gelu_erf_grad_fast), evaluated in
+    float32 numpy with the constants parsed from the header: the documented maximum errors against the exact erf-GELU hold."""
+    import numpy as np
+    from scipy.special import erf
+    src = open(os.path.join(ROOT, "multimodal-aspect-category-sentiment-analysis_b200", "csrc", "common.cuh")).read()
+    c0, c1, c2 = [np.float32(float(re.search(rf"kGeluC{i} = (-?[0-9.eE+-]+)f", src).group(1))) for i in range(3)]
+    x = np.linspace(-12, 12, 480001).astype(np.float32)
+    x2 = np.minimum(x * x, np.float32(64.0))
+    t = np.tanh((x * ((c2 * x2 + c1) * x2 + c0)).astype(np.float64)).astype(np.float32)
+    g = np.float32(0.5) * x * t + np.float32(0.5) * x
+    du = (np.float32(5.0) * c2 * x2 + np.float32(3.0) * c1) * x2 + c0
+    dg = np.float32(0.5) * x * (np.float32(1.0) - t * t) * du + (np.float32(0.5) * t + np.float32(0.5))
+    xd = x.astype(np.float64)
+    Phi = 0.5 * (1 + erf(xd / np.sqrt(2)))
+    assert np.abs(g - xd * Phi).max() < 7e-5
+    assert np.abs(dg - (Phi + xd * np.exp(-0.5 * xd * xd) / np.sqrt(2 * np.pi))).max() < 2e-4

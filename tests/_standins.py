@@ -125,3 +125,25 @@ def install(monkeypatch, pkg):
                      ("layer_tail", layer_tail), ("classifier_ce", classifier_ce)):
         monkeypatch.setattr(Fn, name, fn)
     monkeypatch.setattr(ops, "mask_additive", mask_additive)
+
+
+class _Setter:
+    """Same interface as pytest's monkeypatch.setattr, for spawned worker processes; undo() restores the originals."""
+
+    def __init__(self):
+        self.saved = []
+
+    def setattr(self, obj, name, value):
+        self.saved.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, value)
+
+    def undo(self):
+        for obj, name, old in reversed(self.saved):
+            setattr(obj, name, old)
+        self.saved = []
+
+
+def install_plain(pkg) -> _Setter:
+    st = _Setter()
+    install(st, pkg)
+    return st

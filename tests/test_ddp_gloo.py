@@ -62,3 +62,68 @@ def test_bucketed_reducer_averages_over_ranks():
     for n in grads[0]:
         want = (grads[0][n] + grads[1][n]) / 2
         assert torch.allclose(got[0][n], want, atol=1e-6) and torch.allclose(got[1][n], want, atol=1e-6), n
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The folded FCMF step sharded by sample over 2 ranks (kernel Functions replaced by the CPU stand-ins): the reducer's
+# averaged gradients equal the single-process gradients on the concatenated batch (tier 5).
+def _fcmf_setup():
+    from _util import synth
+    dims = synth.FusionDims(batch=4, aspects=2, seq_len=8, num_imgs=2, num_roi=3)
+    model = pkg().FCMF(None, num_labels=dims.num_labels, num_imgs=dims.num_imgs, num_roi=dims.num_roi)
+    model.load_state_dict(synth.make_params(dims, seed=11), strict=True)
+    model.eval()
+    model.encoder.compute_dtype = torch.float32
+    return dims, model, synth.make_batch(dims, seed=12, mask="bernoulli")
+
+
+def _fcmf_step(model, batch, sl, per, A):
+    _, loss = model.fuse_all_aspects(batch["sequence_output"][sl], batch["visual_embeds_att"][sl], batch["roi_embeds_att"][sl],
+                                     batch["roi_coors"][sl], batch["added_attention_mask"][sl].reshape(per * A, -1),
+                                     batch["labels"][sl], rows="full")
+    loss.backward()
+
+
+def _fcmf_worker(rank, world, port, want_path, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _standins
+    _standins.install_plain(pkg)
+    ddp = pkg("ddp")
+    dims, model, batch = _fcmf_setup()
+    red = ddp.BucketedGradReducer(ddp.fusion_named_parameters(model))
+    per = dims.batch // world
+    sl = slice(rank * per, (rank + 1) * per)                 # a sample's aspects stay on one rank
+    for _ in range(2):                                       # two steps: the flat buckets are re-zeroed in place
+        red.zero_grad()
+        _fcmf_step(model, batch, sl, per, dims.aspects)
+        red.finish()
+    want = torch.load(want_path)
+    gmax = max(float(g.abs().max()) for g in want.values())
+    worst = max(float((p.grad - want[n]).abs().max()) for n, p in model.named_parameters())
+    q.put((rank, worst / gmax))                              # gradients compared in the worker: only a float travels back
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_fcmf_step_gradients_equal_single_process(tmp_path):
+    import _standins
+    st = _standins.install_plain(pkg)
+    try:
+        dims, model, batch = _fcmf_setup()
+        _fcmf_step(model, batch, slice(0, dims.batch), dims.batch, dims.aspects)      # single process, concatenated batch
+        want_path = str(tmp_path / "want.pt")
+        torch.save({n: p.grad.clone() for n, p in model.named_parameters()}, want_path)
+    finally:
+        st.undo()
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fcmf_worker, args=(r, world, port, want_path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(got) == [0, 1] and max(got.values()) < 1e-5, got

@@ -94,10 +94,46 @@ def load() -> C.CDLL:
     return _lib
 
 
+# FCMF_NVTX=1: every C-ABI call and every stage of the folded path (fusion.py) is wrapped in an NVTX range, so an nsys /
+# ncu timeline reads "fcmf_gemm_tn", "fcmf_attn_bwd", "fusion/text->image", ... (tracing hook, off by default).
+NVTX = os.environ.get("FCMF_NVTX", "0") not in ("", "0")
+
+
+class trace:
+    """`with trace("fusion/text->image"):` -- an NVTX range when FCMF_NVTX is set, nothing otherwise."""
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def mark(name: str) -> None:
+    """Instantaneous NVTX marker (stage boundaries of the folded path) when FCMF_NVTX is set."""
+    if NVTX:
+        import torch
+        torch.cuda.nvtx.mark(name)
+
+
 def call(name: str, *args) -> None:
     global launches
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if NVTX:
+        with trace(name):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.fcmf_last_error().decode(errors='replace')}")
     launches += 1

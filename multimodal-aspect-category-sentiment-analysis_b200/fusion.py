@@ -21,7 +21,7 @@ import torch
 
 from . import functional as Fn
 from . import ops
-from ._lib import ENGINE_AUTO
+from ._lib import ENGINE_AUTO, mark
 
 Tensor = torch.Tensor
 PATCH_MASK = 49                    # fcmf_pretraining.py:53
@@ -149,6 +149,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     roi2 = roi_embeds_att[:, :NI].to(dt).reshape(B * NI * NR, Dv)
 
     # ---- once per sample ------------------------------------------------------------------------------
+    mark("fusion: per-sample projections + box attention")
     patches = Fn.linear(vis2, enc.vismap2text.weight, enc.vismap2text.bias, engine=engine)            # [B*NI*P, H]
     w_kv, b_kv = _cat_wb((t2i.attention.self.key, t2i.attention.self.value))
     kv_p = Fn.linear(patches, w_kv, b_kv, engine=engine)                                                # [B*NI*P, 2H]
@@ -167,6 +168,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     w_mm, b_mm = _cat_wb((mm.attention.self.query, mm.attention.self.key, mm.attention.self.value))
 
     # ---- once per (sample, aspect) ----------------------------------------------------------------------
+    mark("fusion: per-(sample, aspect) projections")
     tq = t2i.attention.self.query
     if live:
         cls_rows = sequence_output.to(dt)[:, 0, :]                                                      # [BA, H] strided
@@ -182,6 +184,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     NP = BA * NI
 
     # ---- text -> image branch, all (sample, aspect, image) problems in one launch ------------------------
+    mark("fusion: text->image branch")
     plan1 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("t2i_attn", t2i.attention.self)).add("q", 0, 0, Lq, ix.p2ba, ix.ba2p) \
         .add("k", 1, 0, P, ix.p2bi, ix.bi2p).add("v", 1, H, P, ix.p2bi, ix.bi2p)
     ctx1 = Fn.folded_attention(plan1, (q_t, kv_p), mask_add, None)                                      # [NP*Lq, H]
@@ -192,6 +195,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
                       act="tanh", engine=engine)                                                        # [NP, H]
 
     # ---- text + ROI branch ---------------------------------------------------------------------------------
+    mark("fusion: text+ROI branch")
     if live:
         plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("mm_attn", mm.attention.self)).add("q", 0, 0, 1, ix.p2ba, ix.ba2p) \
             .add("k", 1, 0, L, ix.p2ba, ix.ba2p).add("k", 2, 0, NR, ix.p2bi, ix.bi2p) \
@@ -211,6 +215,7 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
                       act="tanh", engine=engine)                                                        # [NP, H]
 
     # ---- fusion layer: [CLS] + h_1..NI + r_1..NI (fcmf_pretraining.py:127-139), same mm_attention weights ----
+    mark("fusion: 15-token fusion layer")
     fusion = torch.cat((sequence_output.to(dt)[:, 0:1, :], h_img.view(BA, NI, H), r_img.view(BA, NI, H)), 1)
     x = fusion.reshape(BA * F, H)
     qkv_f = Fn.linear(x, w_mm, b_mm, engine=engine)

@@ -178,3 +178,18 @@ def test_gelu_tanh_fit_error_bounds():
     Phi = 0.5 * (1 + erf(xd / np.sqrt(2)))
     assert np.abs(g - xd * Phi).max() < 7e-5
     assert np.abs(dg - (Phi + xd * np.exp(-0.5 * xd * xd) / np.sqrt(2 * np.pi))).max() < 2e-4
+
+
+def test_nvtx_tracing_hook_is_off_by_default_and_harmless():
+    L = pkg("_lib")
+    assert L.NVTX is False or os.environ.get("FCMF_NVTX", "0") not in ("", "0")
+    with L.trace("unit-test range"):
+        pass
+    old = L.NVTX
+    try:
+        L.NVTX = True
+        with L.trace("unit-test range (on)"):            # torch.cuda.nvtx is a no-op without a profiler attached
+            pass
+        assert L.load().fcmf_abi_version() == L.ABI_VERSION
+    finally:
+        L.NVTX = old

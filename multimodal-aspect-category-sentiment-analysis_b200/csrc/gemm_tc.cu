@@ -244,7 +244,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 t = __ldg(b4 + q);
-          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+          const float2 lo = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(t.x, t.y));
+          const float2 hi = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(t.z, t.w));
+          v[4 * q] = lo.x; v[4 * q + 1] = lo.y; v[4 * q + 2] = hi.x; v[4 * q + 3] = hi.y;
         }
       } else {
 #pragma unroll
@@ -262,7 +264,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 gq = gelu_erf_fast2(make_float2(v[j], v[j + 1]));
+        v[j] = gq.x; v[j + 1] = gq.y;
+      }
     } else if (P.epi == FCMF_EPI_TANH) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = tanh_approx(v[j]);
@@ -274,9 +279,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          v[g * 8 + 2 * j] *= gelu_erf_grad_fast(f.x);
-          v[g * 8 + 2 * j + 1] *= gelu_erf_grad_fast(f.y);
+          const float2 d = __fmul2_rn(make_float2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]), gelu_erf_grad_fast2(__bfloat1622float2(h[j])));
+          v[g * 8 + 2 * j] = d.x; v[g * 8 + 2 * j + 1] = d.y;
         }
       }
     }

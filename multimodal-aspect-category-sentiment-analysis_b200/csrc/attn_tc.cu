@@ -202,8 +202,11 @@ struct AtcShared {
   uint32_t tmem;
 };
 
+// 1024-byte alignment of the dynamic shared memory WITHOUT laundering the pointer through an integer: base + offset keeps
+// the shared address space, so the compiler emits LDS / STS (the uintptr_t round trip made every mask load and P store a
+// generic LD / ST, tracked on the long scoreboard).
 __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+  return p + ((1024u - (a_smem_u32(p) & 1023u)) & 1023u);
 }
 
 // One-time CTA setup of the persistent kernels: mbarrier, TMEM columns. Returns the TMEM base address.

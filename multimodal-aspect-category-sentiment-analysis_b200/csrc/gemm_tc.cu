@@ -319,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // base + offset keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* ring = smem;
   uint8_t* stage_epi = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);
@@ -507,7 +507,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // base + offset keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* ring = smem;
   uint8_t* stage_epi = smem + TC2_STAGES * TC2_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);

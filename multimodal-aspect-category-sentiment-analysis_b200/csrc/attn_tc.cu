@@ -327,7 +327,9 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
         }
         red[grp * 128 + trow] = mx;
       }
-      __syncthreads();
+      // the two warps that share a lane quarter (w, w + 4) exchange their row maxima: a 64-thread named barrier instead of a
+      // CTA-wide one (nothing else is shared between the passes; idle pairs skip it together -- wact is uniform per pair)
+      if (wact) asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
       float sum = 0.f;
       if (wact) {
         mx = fmaxf(red[trow], red[128 + trow]);                 // finite: at least key 0 is real and its mask is finite

@@ -187,6 +187,23 @@ int fcmf_vocab_ce_bwd(const void* logits, int64_t ld, const int64_t* labels, int
                       const float* lse, const float* scale, void* dlogits, int64_t ldd, int64_t R, int64_t V,
                       int dtype, void* stream);
 
+/* ---- optimizer tail (run_multimodal_fcmf.py:483-489: clip_grad_norm_(1.0) + torch.optim.AdamW.step) -------------- */
+/* One table entry per parameter tensor (fp32): the 4 parameter groups of the reference only differ in lr / weight_decay. */
+typedef struct {
+  float* p; const float* g; float* m; float* v;   /* parameter, gradient, exp_avg, exp_avg_sq */
+  int64_t n;
+  float lr, wd;
+} fcmf_opt_tensor;
+/* table: DEVICE array of fcmf_opt_tensor; (blk_tensor[b], blk_chunk[b]): block b handles elements
+ * [chunk*8192, (chunk+1)*8192) of that tensor. sumsq[0] = sum of squares of every gradient element. */
+int fcmf_opt_sumsq(const void* table, const int32_t* blk_tensor, const int32_t* blk_chunk, int64_t n_blocks,
+                   float* sumsq, void* stream);
+/* coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6)) (max_norm <= 0: 1); norm_out[0] = sqrt(sumsq[0]) (may be NULL). */
+int fcmf_opt_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
+/* g *= coef[0] (coef may be NULL); AdamW update of every tensor of the table at optimizer step `step` (>= 1). */
+int fcmf_opt_adamw(const void* table, const int32_t* blk_tensor, const int32_t* blk_chunk, int64_t n_blocks,
+                   const float* coef, float beta1, float beta2, float eps, int64_t step, int write_back_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,11 @@ class Dropout(C.Structure):
     _fields_ = [("p", _f32), ("seed", C.c_uint64), ("seed_dev", _vp)]
 
 
+class OptTensor(C.Structure):
+    """fcmf_opt_tensor (include/fcmf_b200.h)."""
+    _fields_ = [("p", _vp), ("g", _vp), ("m", _vp), ("v", _vp), ("n", _i64), ("lr", _f32), ("wd", _f32)]
+
+
 class Seg(C.Structure):
     _fields_ = [("ptr", _vp), ("ld", _i64), ("rows", _i32), ("idx", _vp)]
 
@@ -59,6 +64,9 @@ PROTOTYPES = {
     "fcmf_cls_ce_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
     "fcmf_vocab_ce_fwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp],
     "fcmf_vocab_ce_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp],
+    "fcmf_opt_sumsq": [_vp, _vp, _vp, _i64, _vp, _vp],
+    "fcmf_opt_clip_coef": [_vp, _f32, _vp, _vp, _vp],
+    "fcmf_opt_adamw": [_vp, _vp, _vp, _i64, _vp, _f32, _f32, _f32, _i64, C.c_int, _vp],
     "fcmf_cls_ce_bwd": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, C.POINTER(Dropout), C.c_int, _vp],
 }
 

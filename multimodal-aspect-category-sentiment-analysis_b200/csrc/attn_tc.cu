@@ -189,8 +189,10 @@ __device__ __forceinline__ void store_out32(bf16* o, const uint32_t (&r)[32], fl
     uint4 w;
     __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&w);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      hh[j] = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]) * sc, __uint_as_float(r[g * 8 + 2 * j + 1]) * sc);
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __fmul2_rn(make_float2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1])), make_float2(sc, sc));
+      hh[j] = __floats2bfloat162_rn(t.x, t.y);
+    }
     *reinterpret_cast<uint4*>(o + g * 8) = w;
   }
 }
@@ -200,8 +202,11 @@ struct AtcShared {
   uint32_t tmem;
 };
 
+// 1024-byte alignment of the dynamic shared memory WITHOUT laundering the pointer through an integer: base + offset keeps
+// the shared address space, so the compiler emits LDS / STS (the uintptr_t round trip made every mask load and P store a
+// generic LD / ST, tracked on the long scoreboard).
 __device__ __forceinline__ uint8_t* align1k(uint8_t* p) {
-  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+  return p + ((1024u - (a_smem_u32(p) & 1023u)) & 1023u);
 }
 
 // One-time CTA setup of the persistent kernels: mbarrier, TMEM columns. Returns the TMEM base address.
@@ -227,6 +232,12 @@ __device__ __forceinline__ void drop_row32(float (&v)[32], uint32_t rseed, uint3
     v[j + 1] = drop_keep_hi(hsh, thr16) ? v[j + 1] : 0.f;
   }
 }
+
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100): two lanes' worth of IEEE fp32 operations per issue slot. The
+// softmax loops are issue-limited (ncu: 34-42 % of slots, 16-24 warps per SM), and every operation here is the same
+// round-to-nearest fp32 operation as its scalar form, so results do not change.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 // All three kernels are PERSISTENT: a CTA walks over work items (item = blockIdx.x + n * gridDim.x) with its mbarrier and
 // TMEM columns set up once; what an item shares between its tiles (K/V and the mask for the query-tiled kernels) is
@@ -309,18 +320,22 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
-            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale2, m4.x), fmaf(__uint_as_float(r[j + 1]), scale2, m4.y)),
-                                 fmaxf(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z), fmaf(__uint_as_float(r[j + 3]), scale2, m4.w))));
+            const float2 a = __ffma2_rn(u2f2(r[j], r[j + 1]), f2(scale2, scale2), f2(m4.x, m4.y));
+            const float2 b = __ffma2_rn(u2f2(r[j + 2], r[j + 3]), f2(scale2, scale2), f2(m4.z, m4.w));
+            mx = fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(b.x, b.y));
           }
         }
         red[grp * 128 + trow] = mx;
       }
-      __syncthreads();
+      // the two warps that share a lane quarter (w, w + 4) exchange their row maxima: a 64-thread named barrier instead of a
+      // CTA-wide one (nothing else is shared between the passes; idle pairs skip it together -- wact is uniform per pair)
+      if (wact) asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
       float sum = 0.f;
       if (wact) {
         mx = fmaxf(red[trow], red[128 + trow]);                 // finite: at least key 0 is real and its mask is finite
         uint32_t rseed = 0;
         if (DROP) rseed = drop_rowseed(dc.seed, attn_drop_row(a, p, h, row));
+        float2 sum2 = f2(0.f, 0.f);
 #pragma unroll 1
         for (int c = grp; c < NKB * 2; c += 2) {
           uint32_t r[32];
@@ -329,15 +344,16 @@ attn_tc_fwd_kernel(AttnDev a, bf16* __restrict__ ctx, int64_t ldctx, float* __re
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(msk + c * 32 + j);
-            v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, m4.x) - mx);
-            v[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, m4.y) - mx);
-            v[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z) - mx);
-            v[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, m4.w) - mx);
-            sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+            const float2 a = __fadd2_rn(__ffma2_rn(u2f2(r[j], r[j + 1]), f2(scale2, scale2), f2(m4.x, m4.y)), f2(-mx, -mx));
+            const float2 b = __fadd2_rn(__ffma2_rn(u2f2(r[j + 2], r[j + 3]), f2(scale2, scale2), f2(m4.z, m4.w)), f2(-mx, -mx));
+            v[j] = ex2_approx(a.x); v[j + 1] = ex2_approx(a.y);
+            v[j + 2] = ex2_approx(b.x); v[j + 3] = ex2_approx(b.y);
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(f2(v[j], v[j + 1]), f2(v[j + 2], v[j + 3])));
           }
           if (DROP) drop_row32(v, rseed, (uint32_t)(c * 32), dc.thr16);    // the denominator keeps the dropped terms
           store_row32(Pblk(c >> 1), trow, (c & 1) * 32, v);
         }
+        sum = sum2.x + sum2.y;
         red[256 + grp * 128 + trow] = sum;
       }
       a_fence_async();
@@ -482,15 +498,16 @@ attn_tc_dq_kernel(AttnDev a, const bf16* __restrict__ ctx, int64_t ldctx, const 
             uint32_t h0 = 0, h1 = 0;
             if (DROP) { h0 = drop_pair(rseed, (uint32_t)(b * 64 + grp * 32 + j)); h1 = drop_pair(rseed, (uint32_t)(b * 64 + grp * 32 + j + 2)); }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float pj = ex2_approx(fmaf(__uint_as_float(rs[j + u]), scale2, mm[u]) - l2);
-              float dp = __uint_as_float(rp[j + u]);
+            for (int u = 0; u < 4; u += 2) {
+              const float2 x = __fadd2_rn(__ffma2_rn(u2f2(rs[j + u], rs[j + u + 1]), f2(scale2, scale2), f2(mm[u], mm[u + 1])), f2(-l2, -l2));
+              const float2 pj = f2(ex2_approx(x.x), ex2_approx(x.y));
+              float2 dp = u2f2(rp[j + u], rp[j + u + 1]);
               if (DROP) {
                 const uint32_t hh = u < 2 ? h0 : h1;
-                const bool keep = (u & 1) ? drop_keep_hi(hh, dc.thr16) : drop_keep_lo(hh, dc.thr16);
-                dp = keep ? dp * keep_sc : 0.f;            // dP = keep/(1-p) * (dO . v_j)
+                dp = __fmul2_rn(dp, f2(drop_keep_lo(hh, dc.thr16) ? keep_sc : 0.f, drop_keep_hi(hh, dc.thr16) ? keep_sc : 0.f));   // dP = keep/(1-p) * (dO . v_j)
               }
-              v[j + u] = pj * (dp - dl);
+              const float2 ds = __fmul2_rn(pj, __fadd2_rn(dp, f2(-dl, -dl)));
+              v[j + u] = ds.x; v[j + u + 1] = ds.y;
             }
           }
           store_row32(Ds, trow, grp * 32, v);
@@ -610,17 +627,22 @@ attn_tc_dkv_kernel(AttnDev a, const bf16* __restrict__ dctx, int64_t lddctx, con
         a_tmem_ld32(tS + lane_addr + grp * 32, rs);
         a_tmem_ld32(tP + lane_addr + grp * 32, rp);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 32; j += 2) {
           const int qi = b * 64 + grp * 32 + j;
-          const float pj = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, mk) - ls[qi]);   // 0 for padded queries (ls = +inf)
-          float pd = pj, dp = __uint_as_float(rp[j]);
+          const float2 l2 = *reinterpret_cast<const float2*>(ls + qi), d2 = *reinterpret_cast<const float2*>(dls + qi);
+          const float2 x = __fadd2_rn(__ffma2_rn(u2f2(rs[j], rs[j + 1]), f2(scale2, scale2), f2(mk, mk)), f2(-l2.x, -l2.y));
+          const float2 pj = f2(ex2_approx(x.x), ex2_approx(x.y));                 // 0 for padded queries (ls = +inf)
+          float2 pd = pj, dp = u2f2(rp[j], rp[j + 1]);
           if (DROP) {
-            const bool keep = ((mix32(rsd[qi] + kpair) >> kshift) & 0xffffu) >= dc.thr16;
-            pd = keep ? pj * dc.inv_keep : 0.f;          // dropped probability: dV = P_drop^T . dO
-            dp = keep ? dp * dc.inv_keep : 0.f;
+            const bool k0 = ((mix32(rsd[qi] + kpair) >> kshift) & 0xffffu) >= dc.thr16;
+            const bool k1 = ((mix32(rsd[qi + 1] + kpair) >> kshift) & 0xffffu) >= dc.thr16;
+            const float2 ks = f2(k0 ? dc.inv_keep : 0.f, k1 ? dc.inv_keep : 0.f);
+            pd = __fmul2_rn(pj, ks);                       // dropped probability: dV = P_drop^T . dO
+            dp = __fmul2_rn(dp, ks);
           }
-          pv[j] = pd;
-          dsv[j] = pj * (dp - dls[qi]);
+          const float2 ds = __fmul2_rn(pj, __fadd2_rn(dp, f2(-d2.x, -d2.y)));
+          pv[j] = pd.x; pv[j + 1] = pd.y;
+          dsv[j] = ds.x; dsv[j + 1] = ds.y;
         }
         store_row32(Pt, trow, grp * 32, pv);
         store_row32(St, trow, grp * 32, dsv);

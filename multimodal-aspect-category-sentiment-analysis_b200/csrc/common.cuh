@@ -169,6 +169,28 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {       // x * Phi(x): 6
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// the same two functions on PAIRS (FFMA2 / FMUL2 / FADD2: one issue slot per two elements; identical fp32 results)
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 xx = __fmul2_rn(x, x);
+  const float2 x2 = make_float2(fminf(xx.x, 64.0f), fminf(xx.y, 64.0f));
+  const float2 p = __ffma2_rn(__ffma2_rn(make_float2(kGeluC2, kGeluC2), x2, make_float2(kGeluC1, kGeluC1)), x2, make_float2(kGeluC0, kGeluC0));
+  const float2 u = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+__device__ __forceinline__ float2 gelu_erf_grad_fast2(float2 x) {
+  const float2 xx = __fmul2_rn(x, x);
+  const float2 x2 = make_float2(fminf(xx.x, 64.0f), fminf(xx.y, 64.0f));
+  const float2 p = __ffma2_rn(__ffma2_rn(make_float2(kGeluC2, kGeluC2), x2, make_float2(kGeluC1, kGeluC1)), x2, make_float2(kGeluC0, kGeluC0));
+  const float2 u = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 du = __ffma2_rn(__ffma2_rn(make_float2(5.0f * kGeluC2, 5.0f * kGeluC2), x2, make_float2(3.0f * kGeluC1, 3.0f * kGeluC1)), x2,
+                               make_float2(kGeluC0, kGeluC0));
+  const float2 sech2 = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.0f, 1.0f));
+  const float2 a = __ffma2_rn(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(__fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), sech2), du, a);
+}
 __device__ __forceinline__ float gelu_erf_grad_fast(float x) {  // Phi(x) + x * phi(x) as the derivative of the fit: 12 FP32 ops + 1 MUFU
   const float x2 = fminf(x * x, 64.0f);
   const float t = tanh_approx(x * fmaf(fmaf(kGeluC2, x2, kGeluC1), x2, kGeluC0));

@@ -244,7 +244,9 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 t = __ldg(b4 + q);
-          v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+          const float2 lo = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(t.x, t.y));
+          const float2 hi = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(t.z, t.w));
+          v[4 * q] = lo.x; v[4 * q + 1] = lo.y; v[4 * q + 2] = hi.x; v[4 * q + 3] = hi.y;
         }
       } else {
 #pragma unroll
@@ -262,7 +264,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 gq = gelu_erf_fast2(make_float2(v[j], v[j + 1]));
+        v[j] = gq.x; v[j + 1] = gq.y;
+      }
     } else if (P.epi == FCMF_EPI_TANH) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = tanh_approx(v[j]);
@@ -274,9 +279,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& P, const CUtensorM
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&w);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          v[g * 8 + 2 * j] *= gelu_erf_grad_fast(f.x);
-          v[g * 8 + 2 * j + 1] *= gelu_erf_grad_fast(f.y);
+          const float2 d = __fmul2_rn(make_float2(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]), gelu_erf_grad_fast2(__bfloat1622float2(h[j])));
+          v[g * 8 + 2 * j] = d.x; v[g * 8 + 2 * j + 1] = d.y;
         }
       }
     }
@@ -315,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // base + offset keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* ring = smem;
   uint8_t* stage_epi = smem + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);
@@ -503,7 +507,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX, const TcParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // base + offset keeps the shared address space (LDS/STS, not generic LD/ST)
   uint8_t* ring = smem;
   uint8_t* stage_epi = smem + TC2_STAGES * TC2_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_epi + TC_EPI_SMEM);

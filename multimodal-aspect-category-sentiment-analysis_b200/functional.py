@@ -99,13 +99,13 @@ class _LayerTail(Function):
     @staticmethod
     def forward(ctx, a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor],
                 wo, bo, g1, b1, w1, bi1, w2, bi2, g2, b2, engine: int, drop1: Optional[ops.Drop], drop2: Optional[ops.Drop],
-                out_every: int):
+                out_every: int, eps: float):
         dt = a.dtype
         d = ops.gemm_tn(a, ops.cast_matrix(wo, dt), bo, EPI_NONE, engine=engine)
-        x1, mean1, rstd1 = ops.ln_fwd(d, res_src, res_idx, g1, b1, drop=drop1)      # LN(dropout(dense) + residual)
+        x1, mean1, rstd1 = ops.ln_fwd(d, res_src, res_idx, g1, b1, eps, drop=drop1)  # LN(dropout(dense) + residual)
         g, pre = ops.gemm_tn(x1, ops.cast_matrix(w1, dt), bi1, EPI_GELU, engine=engine, want_aux=True)
         o = ops.gemm_tn(g, ops.cast_matrix(w2, dt), bi2, EPI_NONE, engine=engine)
-        y, mean2, rstd2 = ops.ln_fwd(o, x1, None, g2, b2, drop=drop2)
+        y, mean2, rstd2 = ops.ln_fwd(o, x1, None, g2, b2, eps, drop=drop2)
         ctx.engine, ctx.drop1, ctx.drop2, ctx.out_every = engine, drop1, drop2, out_every
         ctx.save_for_backward(a, res_src, res_idx, res_inv, wo, g1, w1, w2, g2, d, x1, pre, g, o, mean1, rstd1, mean2, rstd2)
         if out_every > 1:            # the caller consumes rows 0, out_every, ... only (token 0 of every problem): hand out that view
@@ -135,19 +135,19 @@ class _LayerTail(Function):
                 dres = ds1
             else:
                 dres = ops.gather_sum_rows(ds1, res_inv, res_src.shape[0], res_inv.shape[1])
-        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None, None, None, None
+        return da, dres, None, None, dwo, dbo, dg1, db1, dw1, dbi1, dw2, dbi2, dg2, db2, None, None, None, None, None
 
 
 def layer_tail(a: Tensor, res_src: Tensor, res_idx: Optional[Tensor], res_inv: Optional[Tensor], params: Sequence[Tensor],
                engine: int = ENGINE_AUTO, drop1: Optional[ops.Drop] = None, drop2: Optional[ops.Drop] = None,
-               out_every: int = 0) -> Tensor:
+               out_every: int = 0, eps: float = ops.LN_EPS) -> Tensor:
     """params = (Wo, bo, ln1.w, ln1.b, W1, b1, W2, b2, ln2.w, ln2.b). Row m of `a` takes residual row
     res_idx[m] of res_src (identity when res_idx is None); res_inv [rows(res_src), G] lists, for every residual
     row, the rows of `a` that used it (-1 padded) so that the backward reduction needs no atomics.
     drop1 / drop2: hidden dropout of BertSelfOutput / BertOutput (mm_modeling.py:278, 326), mask row = row of `a`.
     out_every > 1: every row is computed, but only rows 0, out_every, 2*out_every, ... are returned ([rows/out_every, H], a
     view) -- what BertPooler reads of a per-image branch; the backward pass then takes a compact gradient."""
-    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine, drop1, drop2, out_every)
+    return _LayerTail.apply(a, res_src, res_idx, res_inv, *params, engine, drop1, drop2, out_every, eps)
 
 
 # ------------------------------------------------------------------------------------------------- attention

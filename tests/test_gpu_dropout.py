@@ -217,6 +217,27 @@ def test_train_mode_step_bf16_tensor_core_engines(rows):
         assert rel_err_floor(v.grad, r_grads[k], 1e-2 * gmax) < 8e-2, k
 
 
+@pytest.mark.parametrize("rows", ["full", "live"])
+def test_train_mode_step_bf16_at_config_shape(rows):
+    """The headline mode of bench.py -- train(), bf16, tcgen05 engines -- at the measured SHAPE (L = 170, 7 images x 49
+    patches, 4 ROIs: two query tiles, three key blocks in the text+ROI attention) against the fp32 oracle fed the same masks."""
+    dims = synth.FusionDims(batch=2, aspects=2, seq_len=170, num_imgs=7, num_roi=4)
+    params = synth.make_params(dims, seed=31)
+    batch = synth.make_batch(dims, seed=32, mask="bernoulli")
+    model = build_model(dims, params, torch.bfloat16, rows, L.ENGINE_AUTO).train()
+    seed = 0xC0FFEE
+    logits, loss, dseq = _train_step(model, batch, dims, rows, seed)
+    r_logits, r_loss, r_dseq, r_grads = _oracle_train_step(params, batch, dims, seed, rows == "live")
+    assert rel_err(logits, r_logits) < 2e-2
+    assert rel_err(dseq.float(), r_dseq) < 6e-2
+    gmax = max(float(g.abs().max()) for g in r_grads.values() if g is not None)
+    for k, v in model.named_parameters():
+        assert torch.isfinite(v.grad).all(), k
+        if ".WGs." in k or k.endswith("key.bias") or k.endswith("box_head.linears.1.bias"):
+            continue
+        assert rel_err_floor(v.grad, r_grads[k], 1e-2 * gmax) < 8e-2, k
+
+
 def test_default_seeding_follows_torch_manual_seed_and_graph_replays_redraw():
     dims = synth.FusionDims(batch=2, aspects=2, seq_len=24, num_imgs=2, num_roi=3)
     params = synth.make_params(dims, seed=5)

@@ -168,3 +168,51 @@ def test_missing_inputs_raise_like_the_reference_would():
     with pytest.raises(RuntimeError, match="shorter"):
         model.encoder.fuse(seq, b["visual_embeds_att"].cuda(), b["roi_embeds_att"].cuda(), b["roi_coors"].cuda(),
                            b["added_attention_mask"][:, 0, :20].cuda())
+
+
+# ---- the MEASURED configuration's shape family on the MEASURED engine (bf16, tcgen05 GEMMs + tcgen05 attention) --------------
+# bench.py times L=170 / NI=7 / NR=4 / S=174 in bf16 with ENGINE_AUTO; these cases run exactly those kernel variants (three
+# key blocks in the text+ROI attention, two query tiles, the CTA-pair GEMM) at model level against the reference's goldens.
+@pytest.mark.parametrize("rows", ["full", "live"])
+@pytest.mark.parametrize("name", ["base_cfg1_b1", "large_small"])
+def test_bf16_tcgen05_matches_reference_golden(name, rows):
+    z, dims = load_golden(name)
+    params, batch = golden_inputs(z, dims)
+    model = build_model(dims, params, torch.bfloat16, rows, L.ENGINE_AUTO)
+    logits, loss, dseq = run_folded(model, batch, dims, rows)
+    assert rel_err(logits, torch.from_numpy(z["logits"])) < 2e-2
+    assert abs(loss.item() - float(z["loss"])) < 2e-2 * max(1.0, abs(float(z["loss"])))
+    stride = int(z["sample_stride"])
+    gold = torch.from_numpy(z["d_sequence_output"]).reshape(-1)
+    got = dseq.float().reshape(-1).cpu() if gold.numel() == dseq.numel() else golden_sample(dseq.float(), stride)
+    assert rel_err(got, gold) < 6e-2
+    floor = 1e-2 * grad_scale(z)
+    for k, v in model.named_parameters():
+        assert torch.isfinite(v.grad).all(), k
+        if ".WGs." in k:
+            continue
+        assert rel_err_floor(golden_sample(v.grad, stride), torch.from_numpy(z["gsample/" + k]), floor) < 8e-2, k
+
+
+@pytest.mark.parametrize("rows", ["full", "live"])
+def test_bf16_argmax_at_config2_shape(rows):
+    """A = 6 aspects folded, L = 170, 7 images x 49 patches, 4 ROIs, B = 32 (BASELINE config 2's shape at half the batch):
+    2e-2 relative on logits and argmax agreement on every decided row of every aspect."""
+    from oracle import fcmf_oracle as O
+    dims = synth.FusionDims(batch=32, aspects=6, seq_len=170, num_imgs=7, num_roi=4)
+    params = synth.make_params(dims, seed=9)
+    batch = synth.make_batch(dims, seed=13, mask="bernoulli")
+    with torch.no_grad():
+        ref, _ = O.aspect_loop(batch["sequence_output"], batch["visual_embeds_att"], batch["roi_embeds_att"],
+                               batch["roi_coors"], batch["added_attention_mask"], batch["labels"], params,
+                               dims.heads, dims.num_imgs, dims.num_roi)
+    model = build_model(dims, params, torch.bfloat16, rows, L.ENGINE_AUTO)
+    logits, loss, dseq = run_folded(model, batch, dims, rows)
+    assert rel_err(logits, ref) < 2e-2
+    top2 = ref.topk(2, -1).values
+    decided = (top2[..., 0] - top2[..., 1]) > 2e-2 * ref.abs().max()
+    agree = (logits.argmax(-1).cpu() == ref.argmax(-1))
+    for a in range(dims.aspects):
+        m = decided[:, a]
+        assert m.sum() > 0 and agree[:, a][m].float().mean().item() >= 0.999
+    assert torch.isfinite(dseq.float()).all()

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FCMF_ABI_VERSION 2
+#define FCMF_ABI_VERSION 3
 
 enum { FCMF_F32 = 0, FCMF_BF16 = 1 };
 enum { FCMF_ERR_ARG = -1, FCMF_ERR_CUDA = -2, FCMF_ERR_UNSUPPORTED = -3 };
@@ -125,6 +125,8 @@ typedef struct {
   const void* ptr;      /* NULL => segment absent */
   int64_t ld;           /* row stride, elements */
   int32_t rows;         /* rows per group */
+  int32_t groups;       /* number of groups the tensor holds (idx values lie in [0, groups)); 0 = unknown: the TMA-fed
+                           attention kernels then are not used (they need the extent for their tensor maps) */
   const int32_t* idx;   /* [NP] group index of problem p; NULL => p */
 } fcmf_seg;
 

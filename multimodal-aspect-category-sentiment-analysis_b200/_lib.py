@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfcmf_b200.so")
 
-ABI_VERSION = 2               # FCMF_ABI_VERSION of include/fcmf_b200.h
+ABI_VERSION = 3               # FCMF_ABI_VERSION of include/fcmf_b200.h
 F32, BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_TANH, EPI_DGELU = 0, 1, 2, 3
@@ -30,7 +30,7 @@ class OptTensor(C.Structure):
 
 
 class Seg(C.Structure):
-    _fields_ = [("ptr", _vp), ("ld", _i64), ("rows", _i32), ("idx", _vp)]
+    _fields_ = [("ptr", _vp), ("ld", _i64), ("rows", _i32), ("groups", _i32), ("idx", _vp)]
 
 
 class AttnDesc(C.Structure):

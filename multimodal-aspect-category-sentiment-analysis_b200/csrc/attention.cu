@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "attn.h"
 #include <atomic>
+#include <stdlib.h>
 
 namespace fcmf {
 
@@ -218,13 +219,17 @@ attn_bwd_dkv_kernel(AttnDev a, const T* __restrict__ dctx, int64_t lddctx, const
 
 static std::atomic<int> g_attn_engine{0};
 int attn_engine() { return g_attn_engine.load(std::memory_order_relaxed); }
+bool attn_ws_enabled() {
+  static const bool on = [] { const char* e = getenv("FCMF_ATTN_WS"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 static int to_dev(const fcmf_attn_desc* d, AttnDev* o) {
   FCMF_CHECK_ARG(d != nullptr, "attn: null descriptor");
   for (int s = 0; s < 2; ++s) {
-    o->q[s] = {d->q[s].ptr, d->q[s].ld, d->q[s].ptr ? d->q[s].rows : 0, d->q[s].idx};
-    o->k[s] = {d->k[s].ptr, d->k[s].ld, d->k[s].ptr ? d->k[s].rows : 0, d->k[s].idx};
-    o->v[s] = {d->v[s].ptr, d->v[s].ld, d->v[s].ptr ? d->v[s].rows : 0, d->v[s].idx};
+    o->q[s] = {d->q[s].ptr, d->q[s].ld, d->q[s].ptr ? d->q[s].rows : 0, d->q[s].groups, d->q[s].idx};
+    o->k[s] = {d->k[s].ptr, d->k[s].ld, d->k[s].ptr ? d->k[s].rows : 0, d->k[s].groups, d->k[s].idx};
+    o->v[s] = {d->v[s].ptr, d->v[s].ld, d->v[s].ptr ? d->v[s].rows : 0, d->v[s].groups, d->v[s].idx};
   }
   FCMF_CHECK_ARG(d->q[0].ptr && d->k[0].ptr && d->v[0].ptr, "attn: segment 0 of q/k/v is required");
   FCMF_CHECK_ARG(o->k[0].rows == o->v[0].rows && o->k[1].rows == o->v[1].rows, "attn: k/v segment rows differ");
@@ -267,6 +272,7 @@ extern "C" int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, 
     const int eng = attn_engine();
     const bool ok = dtype == FCMF_BF16 && attn_tc_supported(a, ldctx, ctx);
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_fwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
+    if (ok && eng != FCMF_ENGINE_SIMT && attn_ws_enabled() && attn_ws_supported(a, ldctx, ctx)) return attn_ws_fwd(a, ctx, ldctx, lse, as_stream(stream));
     if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_fwd(a, ctx, ldctx, lse, as_stream(stream));
     if (eng != FCMF_ENGINE_SIMT && attn_q1_supported(a)) return attn_q1_fwd(a, ctx, ldctx, lse, dtype, as_stream(stream));
   }
@@ -297,6 +303,9 @@ extern "C" int fcmf_attn_bwd(const fcmf_attn_desc* d, const void* ctx, int64_t l
     const int eng = attn_engine();
     const bool ok = dtype == FCMF_BF16 && dbias == nullptr && attn_tc_supported(a, ldctx, ctx) && (lddctx % 8) == 0;
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_bwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
+    if (ok && eng != FCMF_ENGINE_SIMT && attn_ws_enabled() && attn_ws_bwd_supported(a, ldctx, ctx, lddctx) &&
+        (reinterpret_cast<uintptr_t>(dctx) & 15u) == 0)
+      return attn_ws_bwd(a, ctx, ldctx, dctx, lddctx, lse, dq, dk, dv, st);
     if (ok && eng != FCMF_ENGINE_SIMT) return attn_tc_bwd(a, ctx, ldctx, dctx, lddctx, lse, delta, dq, dk, dv, st);
     if (eng != FCMF_ENGINE_SIMT && dbias == nullptr && attn_q1_supported(a)) return attn_q1_bwd(a, ctx, ldctx, dctx, lddctx, lse, dq, dk, dv, dtype, st);
   }

@@ -4,7 +4,7 @@
 
 namespace fcmf {
 
-struct SegDev { const void* ptr; int64_t ld; int rows; const int32_t* idx; };
+struct SegDev { const void* ptr; int64_t ld; int rows; int groups; const int32_t* idx; };
 struct AttnDev {
   SegDev q[2], k[2], v[2];
   const float* mask_add; int64_t ld_mask; int mask_div;
@@ -34,6 +34,13 @@ bool attn_tc_supported(const AttnDev& a, int64_t ldctx, const void* ctx);
 int attn_tc_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStream_t st);
 int attn_tc_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
                 float* delta, void* dq, void* dk, void* dv, cudaStream_t st);
+// warp-specialised TMA-fed tcgen05 engine (attn_ws.cu): bf16, head_dim 64, padded key length <= 192
+bool attn_ws_supported(const AttnDev& a, int64_t ldctx, const void* ctx);
+int attn_ws_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, cudaStream_t st);
+bool attn_ws_bwd_supported(const AttnDev& a, int64_t ldctx, const void* ctx, int64_t lddctx);
+int attn_ws_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
+                void* dq, void* dk, void* dv, cudaStream_t st);
+bool attn_ws_enabled();  // FCMF_ATTN_WS=0 in the environment keeps the cp.async kernels of attn_tc.cu (A/B measurements)
 int attn_engine();      // 0 auto, 1 CUDA-core, 2 tcgen05 (fcmf_set_attn_engine)
 
 // single-query kernels (attn_q1.cu): Lq == 1, no per-pair bias, either dtype

@@ -97,7 +97,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+# ------------------------------------------------------------------------------------------------ CPU legs (reference / oracle)
+REF_BATCH = 4          # the reference's CPU step is timed at B = 4, always (comparable across runs)
+
+
 def cpu_step_fn(dims, torch):
     """The reference's CPU implementation of the path, restated (oracle port): per-aspect, per-image loops, fp32."""
     from oracle import fcmf_oracle as O
@@ -118,23 +121,99 @@ def cpu_step_fn(dims, torch):
     return step
 
 
-def cpu_baseline(torch, synth, base_dims, budget_s=20.0):
+def reference_available() -> bool:
+    try:
+        from oracle import build_ref
+        return build_ref.available()
+    except Exception:
+        return False
+
+
+def reference_step_fn(dims, torch, train: bool):
+    """THE REFERENCE ITSELF (unmodified modules snapshotted into oracle/_ref by oracle/build_ref.py): ``FCMF`` with the text
+    encoder stubbed by a leaf ``sequence_output`` (fusion-only, the path this repository replaces), step body = the loop of
+    run_multimodal_fcmf.py:462-481 -- one model(...) call per aspect, summed CrossEntropyLoss, one backward()."""
+    import tempfile
+    pkg = importlib.import_module(PKG)
+    mm = importlib.import_module("oracle._ref.fcmf_framework.mm_modeling")
+    if (mm.HIDDEN_SIZE, mm.NUM_ATTENTION_HEADS, mm.INTERMEDIATE_SIZE) != (dims.hidden, dims.heads, dims.inter):
+        if "oracle._ref.fcmf_framework.fcmf_multimodal" in sys.modules:
+            raise RuntimeError("the reference's model dimensions are import-time constants (mm_modeling.py:21-30): one size per process")
+        mm.HIDDEN_SIZE, mm.NUM_ATTENTION_HEADS, mm.INTERMEDIATE_SIZE = dims.hidden, dims.heads, dims.inter
+    FCMF = importlib.import_module("oracle._ref.fcmf_framework.fcmf_multimodal").FCMF
+    from transformers import XLMRobertaConfig, XLMRobertaModel
+    with tempfile.TemporaryDirectory() as d:                   # a tiny local text encoder so that the ctor runs; stubbed below
+        XLMRobertaModel(XLMRobertaConfig(vocab_size=64, hidden_size=32, num_hidden_layers=1, num_attention_heads=2,
+                                         intermediate_size=64, max_position_embeddings=40, type_vocab_size=1,
+                                         pad_token_id=1)).save_pretrained(d)
+        model = FCMF(d, num_labels=dims.num_labels, num_imgs=dims.num_imgs, num_roi=dims.num_roi)
+
+    class StubText(torch.nn.Module):
+        def forward(self, input_ids, token_type_ids, attention_mask):
+            return input_ids, None, None
+    model.encoder.bert = StubText()
+    missing, unexpected = model.load_state_dict(pkg.synth.make_params(dims, seed=42), strict=False)
+    assert not unexpected, unexpected
+    model = model.train() if train else model.eval()
+    batch = pkg.synth.make_batch(dims, seed=1234)
+    seq = batch["sequence_output"].requires_grad_(True)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        seq.grad = None
+        total = 0
+        for a in range(dims.aspects):
+            logits = model(input_ids=seq[:, a], token_type_ids=None, attention_mask=None,
+                           added_attention_mask=batch["added_attention_mask"][:, a],
+                           visual_embeds_att=batch["visual_embeds_att"], roi_embeds_att=batch["roi_embeds_att"],
+                           roi_coors=batch["roi_coors"])
+            total = total + crit(logits, batch["labels"][:, a])
+        total.backward()
+        return float(total.detach())
+    return step
+
+
+def _time_steps(step, warmup, steps):
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return sum(ts) / len(ts), ts[len(ts) // 2]
+
+
+def cpu_leg(torch, synth, base_dims, warmup, steps, train):
+    """(mean s/step, median s/step, kind, description) of the reference's CPU step at B = REF_BATCH."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    d1 = synth.FusionDims(**{**base_dims.to_dict(), "batch": 1})
-    s1 = cpu_step_fn(d1, torch)
-    t0 = time.perf_counter(); s1(); t1 = time.perf_counter() - t0            # warm-up + calibration, B=1
-    b = max(1, min(4, int(budget_s / max(t1, 1e-3) / 2)))
-    d = synth.FusionDims(**{**base_dims.to_dict(), "batch": b})
-    step = cpu_step_fn(d, torch)
-    n = 2
-    t0 = time.perf_counter()
-    for _ in range(n):
-        step()
-    dt = (time.perf_counter() - t0) / n
-    return {"value": b / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle/fcmf_oracle.py (restatement of the reference's per-aspect/per-image PyTorch path), fp32, "
-                      f"batch {b} of the same shapes, {n} timed steps after 1 warm-up, {dt:.2f} s/step"}
+    d = synth.FusionDims(**{**base_dims.to_dict(), "batch": REF_BATCH})
+    if reference_available():
+        step = reference_step_fn(d, torch, train)
+        kind = "reference"
+        what = ("the UNMODIFIED reference modules (oracle/_ref snapshot of /root/reference/fcmf_framework), fusion-only FCMF "
+                "(text encoder stubbed), per-aspect loop of run_multimodal_fcmf.py:462-481")
+    else:
+        step = cpu_step_fn(d, torch)
+        kind = "port"
+        what = "oracle/fcmf_oracle.py (restatement of the reference's per-aspect/per-image PyTorch path; oracle/_ref absent)"
+        train = False
+    mean, med = _time_steps(step, warmup, steps)
+    return mean, med, kind, (f"{what}, fp32, batch {REF_BATCH} of the same shapes, {'train()' if train else 'eval()'}, "
+                             f"{steps} timed steps after {warmup} warm-up, {mean:.2f} s/step, {torch.get_num_threads()} threads of "
+                             f"{cores} cores")
+
+
+def cpu_baseline(torch, synth, base_dims):
+    mean, med, kind, sample = cpu_leg(torch, synth, base_dims, 1, 2, train=True)
+    out = {"value": REF_BATCH / mean, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample}
+    if kind == "reference":
+        m2, _, _, s2 = cpu_leg(torch, synth, base_dims, 1, 2, train=False)
+        out["eval_mode"] = {"value": REF_BATCH / m2, "unit": UNIT, "sample": s2}
+    return out
 
 
 def eager_device_baseline(torch, synth, dims, dev, steps=2):
@@ -170,40 +249,31 @@ def eager_device_baseline(torch, synth, dims, dev, steps=2):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path for this workload (oracle port; /root/reference is a Python
-    package that cannot travel to the GPU box), all host threads, a bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of this workload -- the unmodified modules from oracle/_ref
+    (kind "reference"; the oracle port only if the snapshot is absent) -- on all host threads, at the FIXED batch
+    REF_BATCH = 4, train() mode like the headline of the GPU arm, eval() beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     pkg = importlib.import_module(PKG)
     synth = pkg.synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    base = synth.FusionDims(batch=args.batch, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
-    d1 = synth.FusionDims(**{**base.to_dict(), "batch": 1})
-    s1 = cpu_step_fn(d1, torch)
-    t0 = time.perf_counter(); s1(); t1 = time.perf_counter() - t0
-    total_steps = args.steps + args.warmup
-    b = max(1, min(4, int(150.0 / max(t1, 1e-3) / max(total_steps, 1))))
-    step = s1 if b == 1 else cpu_step_fn(synth.FusionDims(**{**base.to_dict(), "batch": b}), torch)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = b / dt
-    sample = (f"oracle port of the reference CPU path (per-aspect, per-image loops, fp32), batch {b} per step of the same "
-              f"shapes, {torch.get_num_threads()} threads")
+    base = synth.FusionDims(batch=REF_BATCH, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
+    mean, med, kind, sample = cpu_leg(torch, synth, base, args.warmup, args.steps, train=True)
+    val = REF_BATCH / mean
+    other = None
+    if kind == "reference":
+        m2, _, _, s2 = cpu_leg(torch, synth, base, 1, max(2, min(args.steps, 5)), train=False)
+        other = {"mode": "eval", "value": REF_BATCH / m2, "unit": UNIT, "ms_per_step": m2 * 1e3, "sample": s2}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": mean * 1e3, "median_ms_per_step": med * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(base, "exec"), "rows": "exec (everything the reference executes)",
-                   "sample_batch": b, "mode": "dropout off (the oracle port's deterministic path; the reference's own "
-                                             "train() step would add its nn.Dropout work on top)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+                   "sample_batch": REF_BATCH, "mode": "train() (nn.Dropout p=0.1 active)" if kind == "reference" else
+                   "dropout off (oracle port; oracle/_ref snapshot absent)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
+        "other_dropout_mode": other,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 

@@ -23,12 +23,12 @@ namespace fcmf {
 namespace ws {
 
 constexpr int BW_THREADS = 640;
-constexpr int QGS = 3;                          // (Q | dO) tile ring
 constexpr int KVS = 3;                          // (K | V) block ring
 
 struct BwdMaps {
   CUtensorMap q0f, q0t, q1;                     // loads: Q tiles (128 rows)
   CUtensorMap g0f, g0t, g1;                     //        dO tiles (two virtual row segments of [NP][Lq][HD])
+  CUtensorMap o0f, o0t, o1;                     //        O tiles (only when delta comes from dO . O: more than one key block)
   CUtensorMap k0f, k0t, k1;                     //        K blocks (64 rows)
   CUtensorMap v0f, v0t, v1;
   CUtensorMap dq0f, dq0t, dq1;                  // stores
@@ -36,13 +36,19 @@ struct BwdMaps {
   CUtensorMap dv0f, dv0t, dv1;
 };
 
-struct BwdSmem {
+// delta_i = sum_j dO_ij O_ij = sum_j P_ij dP'_ij. With ONE key block (text->image: 49 keys) a team holds the whole row of P
+// and dP' and forms delta itself (one exchange between the two threads of a row): no O traffic at all, ring of three
+// (Q | dO) slots. With more blocks the producer also loads the O tile and two dedicated warps form dO . O from shared
+// memory (and stage lse): two (Q | dO | O) slots -- the same 96 KB.
+template <bool ONEBLK> struct BwdSmem {
+  static constexpr int QGS = ONEBLK ? 3 : 2;
+  static constexpr uint32_t kSlot = (ONEBLK ? 2 : 3) * TILE_B;
   static constexpr uint32_t kPdS0 = 0;                                  // [team][P 16K | dS 16K]
-  static constexpr uint32_t kQG0 = 4 * TILE_B;                          // [slot][Q 16K | dO 16K]
-  static constexpr uint32_t kKV0 = kQG0 + QGS * 2 * TILE_B;             // [slot][K 8K | V 8K]
+  static constexpr uint32_t kQG0 = 4 * TILE_B;                          // [slot][Q 16K | dO 16K (| O 16K)]
+  static constexpr uint32_t kKV0 = kQG0 + QGS * kSlot;                  // [slot][K 8K | V 8K]
   static constexpr uint32_t kMsk0 = kKV0 + KVS * 2 * BLK_B;             // [slot][64] f32 additive key mask, log2 domain
-  static constexpr uint32_t kDlt0 = kMsk0 + KVS * 64 * 4;               // [slot][128] f32 delta
-  static constexpr uint32_t kBar0 = kDlt0 + QGS * 128 * 4;
+  static constexpr uint32_t kDlt0 = kMsk0 + KVS * 64 * 4;               // [slot][delta 128 | lse*log2e 128] f32; ONEBLK: [team][half][128] partial sums
+  static constexpr uint32_t kBar0 = kDlt0 + 3 * 256 * 4;
   static constexpr uint32_t kSmem = kBar0 + 512 + 1024;
 };
 
@@ -67,11 +73,13 @@ __device__ __forceinline__ void team_bar(int e) { asm volatile("bar.sync %0, 256
 // MN-major A operand: 64-element M blocks are `lbo` bytes apart, 8-row (reduction) groups 1024 B apart
 __device__ __forceinline__ uint64_t sdesc_mn(uint32_t saddr, uint32_t lbo_bytes) { return sdesc(saddr, lbo_bytes); }
 
-template <bool DROP>
+template <bool DROP, bool ONEBLK>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, const bf16* __restrict__ ctx, int64_t ldctx,
                    const float* __restrict__ lse) {
-  using S = BwdSmem;
+  using S = BwdSmem<ONEBLK>;
+  constexpr int QGS = S::QGS;
+  constexpr uint32_t SLOT = S::kSlot;
   extern __shared__ uint8_t raw[];
   uint8_t* sm = raw + ((1024u - (s32(raw) & 1023u)) & 1023u);
   uint8_t* PdS = sm + S::kPdS0;
@@ -103,7 +111,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&qg_full[i], 1); mbar_init(&qg_empty[i], 1); mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-      mbar_init(&d_full[i], 64); mbar_init(&d_empty[i], 256);
+      mbar_init(&d_full[i], ONEBLK ? 1 : 64); mbar_init(&d_empty[i], 256);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&pds_full[i], 256); mbar_init(&pds_empty[i], 1);
@@ -129,18 +137,25 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       const int tt = it * n_qt + qt, slot = tt % QGS;
       mbar_wait(&qg_empty[slot], ((tt / QGS) & 1) ^ 1, 1);
       if (lane == 0) {
-        uint8_t* dq_ = QG + slot * 2 * TILE_B;
+        uint8_t* dq_ = QG + slot * SLOT;
         uint8_t* dg_ = dq_ + TILE_B;
+        uint8_t* do_ = dg_ + TILE_B;
         const int r0 = qt * 128;
         const int n0p = min(max(P.ql.rows0p - r0, 0), 128);
         const bool seg1_here = P.ql.rows1 > 0 && P.ql.rows0p >= r0 && P.ql.rows0p < r0 + 128;
-        mbar_expect_tx(&qg_full[slot], 2u * ((uint32_t)n0p * 128u + (seg1_here ? (uint32_t)P.ql.rows1p * 128u : 0u)));
-        if (n0p == 128) { tma3(dq_, &M.q0f, &qg_full[slot], h * 64, r0, gq0); tma3(dg_, &M.g0f, &qg_full[slot], h * 64, r0, p); }
-        else if (n0p > 0) { tma3(dq_, &M.q0t, &qg_full[slot], h * 64, r0, gq0); tma3(dg_, &M.g0t, &qg_full[slot], h * 64, r0, p); }
+        mbar_expect_tx(&qg_full[slot], (ONEBLK ? 2u : 3u) * ((uint32_t)n0p * 128u + (seg1_here ? (uint32_t)P.ql.rows1p * 128u : 0u)));
+        if (n0p == 128) {
+          tma3(dq_, &M.q0f, &qg_full[slot], h * 64, r0, gq0); tma3(dg_, &M.g0f, &qg_full[slot], h * 64, r0, p);
+          if (!ONEBLK) tma3(do_, &M.o0f, &qg_full[slot], h * 64, r0, p);
+        } else if (n0p > 0) {
+          tma3(dq_, &M.q0t, &qg_full[slot], h * 64, r0, gq0); tma3(dg_, &M.g0t, &qg_full[slot], h * 64, r0, p);
+          if (!ONEBLK) tma3(do_, &M.o0t, &qg_full[slot], h * 64, r0, p);
+        }
         if (seg1_here) {
           const int off = (P.ql.rows0p - r0) * 128;
           tma3(dq_ + off, &M.q1, &qg_full[slot], h * 64, 0, gq1);
           tma3(dg_ + off, &M.g1, &qg_full[slot], h * 64, 0, p);
+          if (!ONEBLK) tma3(do_ + off, &M.o1, &qg_full[slot], h * 64, 0, p);
         }
       }
     };
@@ -206,7 +221,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       auto issue_a = [&](const It& c) {
         const int kb = c.it * nkb + c.g, tt = c.it * n_qt + c.qt, e = c.n & 1;
         tc_after();
-        const uint32_t q = s32(QG + (tt % QGS) * 2 * TILE_B), dO = q + TILE_B;
+        const uint32_t q = s32(QG + (tt % QGS) * SLOT), dO = q + TILE_B;
         const uint32_t k = s32(KV + (kb % KVS) * 2 * BLK_B), v = k + BLK_B;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) umma(tm + e * 128, sdesc(q + kk * 32, 16), sdesc(k + kk * 32, 16), idesc(64, 0, 0), kk > 0 ? 1u : 0u);
@@ -217,7 +232,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       auto issue_b = [&](const It& c) {
         const int kb = c.it * nkb + c.g, tt = c.it * n_qt + c.qt, e = c.n & 1;
         tc_after();
-        const uint32_t q = s32(QG + (tt % QGS) * 2 * TILE_B), dO = q + TILE_B;
+        const uint32_t q = s32(QG + (tt % QGS) * SLOT), dO = q + TILE_B;
         const uint32_t k = s32(KV + (kb % KVS) * 2 * BLK_B);
         const uint32_t pimg = s32(PdS + e * 2 * TILE_B), dsimg = pimg + TILE_B;
         const int ks_k = (min(64, P.kl.total - c.g * 64) + 15) >> 4;         // 16-key steps that hold real keys
@@ -251,48 +266,46 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       }
     }
   } else if (warp < 4) {
-    // ===================================================================== delta = rowsum(dO o O), 64 threads
-    // 8 lanes share a row (16 bytes each): O comes straight from global memory as full 128-byte lines, dO from the tile
-    const int w2 = warp - 2, sub = lane >> 3, ch = lane & 7;
-    int it = 0;
-    for (int item = blockIdx.x; item < P.items; item += stride, ++it) {
-      const int p = item / P.heads, h = item - p * P.heads;
-      for (int qt = 0; qt < n_qt; ++qt) {
-        const int tt = it * n_qt + qt, slot = tt % QGS;
-        mbar_wait(&d_empty[slot], ((tt / QGS) & 1) ^ 1, 3);
-        mbar_wait(&qg_full[slot], (tt / QGS) & 1, 4);
-        const uint8_t* dO = QG + slot * 2 * TILE_B + TILE_B;
+    // ===================================================================== delta = rowsum(dO o O) and lse*log2e, 64 threads
+    // (more than one key block only) thread t owns tile rows t and t + 64; O and dO tiles are read from shared memory
+    if (!ONEBLK) {
+      const int t2 = (warp - 2) * 32 + lane;
+      int it = 0;
+      for (int item = blockIdx.x; item < P.items; item += stride, ++it) {
+        const int p = item / P.heads, h = item - p * P.heads;
+        for (int qt = 0; qt < n_qt; ++qt) {
+          const int tt = it * n_qt + qt, slot = tt % QGS;
+          float l2v[2];
 #pragma unroll
-        for (int half8 = 0; half8 < 2; ++half8) {
-          uint4 ov[8];
-          int rows[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = w2 * 64 + (half8 * 8 + i) * 4 + sub;
-            const int lrow = logical_row(P.ql, qt * 128 + r);
-            rows[i] = lrow;
-            ov[i] = make_uint4(0, 0, 0, 0);
-            if (lrow >= 0) ov[i] = *reinterpret_cast<const uint4*>(ctx + ((int64_t)p * P.Lq + lrow) * ldctx + (int64_t)h * 64 + ch * 8);
+          for (int i = 0; i < 2; ++i) {                              // in flight while the tiles land
+            const int lrow = logical_row(P.ql, qt * 128 + t2 + i * 64);
+            l2v[i] = lrow >= 0 ? lse[((int64_t)p * P.heads + h) * P.Lq + lrow] * kLog2e : INFINITY;   // padded rows: P = exp2(. - inf) = 0
           }
+          mbar_wait(&d_empty[slot], ((tt / QGS) & 1) ^ 1, 3);
+          mbar_wait(&qg_full[slot], (tt / QGS) & 1, 4);
+          const uint8_t* dO = QG + slot * SLOT + TILE_B;
+          const uint8_t* O = dO + TILE_B;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = w2 * 64 + (half8 * 8 + i) * 4 + sub;
-            const uint4 gv = *reinterpret_cast<const uint4*>(dO + swz(r, ch));
-            const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
-            const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&gv);
+          for (int i = 0; i < 2; ++i) {
+            const int r = t2 + i * 64;
             float part = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 fo = __bfloat1622float2(ho[j]), fg = __bfloat1622float2(hg[j]);
-              part = fmaf(fo.x, fg.x, fmaf(fo.y, fg.y, part));
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint4 ov = *reinterpret_cast<const uint4*>(O + swz(r, ch));
+              const uint4 gv = *reinterpret_cast<const uint4*>(dO + swz(r, ch));
+              const __nv_bfloat162* ho = reinterpret_cast<const __nv_bfloat162*>(&ov);
+              const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 fo = __bfloat1622float2(ho[j]), fg = __bfloat1622float2(hg[j]);
+                part = fmaf(fo.x, fg.x, fmaf(fo.y, fg.y, part));
+              }
             }
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 4);
-            if (ch == 0) dlt[slot * 128 + r] = rows[i] >= 0 ? part : 0.f;
+            dlt[slot * 256 + r] = part;                              // padded rows: O and dO are zero-filled
+            dlt[slot * 256 + 128 + r] = l2v[i];
           }
+          mbar_arrive(&d_full[slot]);
         }
-        mbar_arrive(&d_full[slot]);
       }
     }
   } else {
@@ -310,6 +323,13 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
     if (DROP) dc = make_drop(P.drop);
     It c{(int)blockIdx.x, 0, 0, 0, 0};
     if (e == 1) next(c, nkb, n_qt, stride);
+    auto load_l2 = [&](const It& x) -> float {                        // ONEBLK: lse of this thread's row, prefetched one iteration ahead
+      if (x.item >= P.items) return INFINITY;
+      const int lr = logical_row(P.ql, x.qt * 128 + trow);
+      const int xp = x.item / P.heads, xh = x.item - xp * P.heads;
+      return lr >= 0 ? lse[((int64_t)xp * P.heads + xh) * P.Lq + lr] * kLog2e : INFINITY;
+    };
+    float l2_next = ONEBLK ? load_l2(c) : 0.f;
     while (c.item < P.items) {
       const int p = c.item / P.heads, h = c.item - p * P.heads;
       const int kb = c.it * nkb + c.g, tt = c.it * n_qt + c.qt, u = c.n >> 1;
@@ -318,56 +338,123 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       const int lrow = logical_row(P.ql, r0 + trow);
       const int wlo = r0 + quad * 32, whi = wlo + 32;
       const bool wact = wlo < P.ql.rows0 || (P.ql.rows1 > 0 && wlo < P.ql.rows0p + P.ql.rows1 && whi > P.ql.rows0p);
-      float l2 = INFINITY, dl = 0.f;                               // padded rows: P = exp2(. - inf) = 0
-      if (lrow >= 0) l2 = lse[((int64_t)p * P.heads + h) * P.Lq + lrow] * kLog2e;
+      float l2 = l2_next, dl = 0.f;
+      if (ONEBLK) {
+        It cn = c;
+        next(cn, nkb, n_qt, stride);
+        if (cn.item < P.items) next(cn, nkb, n_qt, stride);
+        l2_next = load_l2(cn);
+      }
       mbar_wait(&kv_full[kvs], (kb / KVS) & 1, 5);                 // mask slice visible
-      mbar_wait(&d_full[qs], (tt / QGS) & 1, 6);                   // delta visible
-      dl = dlt[qs * 128 + trow];
+      if (!ONEBLK) {
+        mbar_wait(&d_full[qs], (tt / QGS) & 1, 6);                 // delta and lse*log2e of the tile visible
+        dl = dlt[qs * 256 + trow];
+        l2 = dlt[qs * 256 + 128 + trow];
+      }
       mbar_wait(&s_full[e], u & 1, 7);
       tc_after();
       // P' / dS images of this team: consumed by B two iterations ago; staging reads of its TMA stores have finished
       if (st_thread) tma_store_wait_read();
       mbar_wait(&pds_empty[e], (u & 1) ^ 1, 8);
       team_bar(e);
-      if (wact) {
-        const float* m = msk + kvs * 64 + half * 32;
-        uint32_t rseed = 0;
-        if (DROP) rseed = drop_rowseed(dc.seed, ((uint64_t)p * (uint64_t)P.heads + (uint64_t)h) * (uint64_t)P.Lq + (uint64_t)max(lrow, 0));
-        const int x0 = c.g * 64 + half * 32;                       // padded key position of this thread's first column
-        const bool pair_path = x0 + 32 <= P.kl.rows0p;             // inside segment 0: padded position == key index
+      const float* m = msk + kvs * 64 + half * 32;
+      uint32_t rseed = 0;
+      if (DROP) rseed = drop_rowseed(dc.seed, ((uint64_t)p * (uint64_t)P.heads + (uint64_t)h) * (uint64_t)P.Lq + (uint64_t)max(lrow, 0));
+      const int x0 = c.g * 64 + half * 32;                         // padded key position of this thread's first column
+      const bool pair_path = x0 + 32 <= P.kl.rows0p;               // inside segment 0: padded position == key index
+      auto keep2 = [&](int xa, bool& k0, bool& k1) {                // dropout keep bits of the column pair (xa, xa + 1)
+        if (pair_path) {
+          const uint32_t hsh = drop_pair(rseed, (uint32_t)xa);
+          k0 = drop_keep_lo(hsh, dc.thr16); k1 = drop_keep_hi(hsh, dc.thr16);
+        } else {
+          const int xb = xa + 1;
+          k0 = drop_keep(rseed, (uint32_t)(xa < P.kl.rows0p ? xa : xa - gap), dc.thr16);
+          k1 = drop_keep(rseed, (uint32_t)(xb < P.kl.rows0p ? xb : xb - gap), dc.thr16);
+        }
+      };
+      if (!ONEBLK) {
+        if (wact) {
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {                           // two 16-column sub-chunks (register budget: 96)
-          uint32_t rs[16], rp[16];
-          float pv[16], dsv[16];
-          tmem_ld16(tS + sc * 16, rs);
-          tmem_ld16(tP + sc * 16, rp);
-          tmem_ld_wait();
+          for (int sc = 0; sc < 2; ++sc) {                         // two 16-column sub-chunks (register budget)
+            uint32_t rs[16], rp[16];
+            float pv[16], dsv[16];
+            tmem_ld16(tS + sc * 16, rs);
+            tmem_ld16(tP + sc * 16, rp);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float2 m2 = *reinterpret_cast<const float2*>(m + sc * 16 + j);
-            const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, m2.x) - l2);
-            const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), scale2, m2.y) - l2);
-            float d0 = __uint_as_float(rp[j]), d1 = __uint_as_float(rp[j + 1]);
-            float q0 = p0, q1 = p1;
-            if (DROP) {
-              bool k0, k1;
-              const int xa = x0 + sc * 16 + j;
-              if (pair_path) {
-                const uint32_t hsh = drop_pair(rseed, (uint32_t)xa);
-                k0 = drop_keep_lo(hsh, dc.thr16); k1 = drop_keep_hi(hsh, dc.thr16);
-              } else {
-                const int xb = xa + 1;
-                k0 = drop_keep(rseed, (uint32_t)(xa < P.kl.rows0p ? xa : xa - gap), dc.thr16);
-                k1 = drop_keep(rseed, (uint32_t)(xb < P.kl.rows0p ? xb : xb - gap), dc.thr16);
+            for (int j = 0; j < 16; j += 2) {
+              const float2 m2 = *reinterpret_cast<const float2*>(m + sc * 16 + j);
+              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, m2.x) - l2);
+              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), scale2, m2.y) - l2);
+              float d0 = __uint_as_float(rp[j]), d1 = __uint_as_float(rp[j + 1]);
+              float q0 = p0, q1 = p1;
+              if (DROP) {
+                bool k0, k1;
+                keep2(x0 + sc * 16 + j, k0, k1);
+                q0 = k0 ? p0 * dc.inv_keep : 0.f; d0 = k0 ? d0 * dc.inv_keep : 0.f;
+                q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
               }
-              q0 = k0 ? p0 * dc.inv_keep : 0.f; d0 = k0 ? d0 * dc.inv_keep : 0.f;
-              q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
+              pv[j] = q0; pv[j + 1] = q1;
+              dsv[j] = p0 * (d0 - dl); dsv[j + 1] = p1 * (d1 - dl);
             }
-            pv[j] = q0; pv[j + 1] = q1;
-            dsv[j] = p0 * (d0 - dl); dsv[j + 1] = p1 * (d1 - dl);
+            store_row16(pimg, trow, half * 32 + sc * 16, pv);
+            store_row16(dsimg, trow, half * 32 + sc * 16, dsv);
           }
-          store_row16(pimg, trow, half * 32 + sc * 16, pv);
-          store_row16(dsimg, trow, half * 32 + sc * 16, dsv);
+        }
+      } else {
+        // one key block: delta_i = sum_j P_ij dP'_ij from the registers of the two threads that share row i
+        float pk[32];
+        uint32_t kbits = 0xffffffffu;
+        float part = 0.f;
+        float* red = dlt + e * 256;                                 // [half][128]
+        if (wact) {
+#pragma unroll
+          for (int sc = 0; sc < 2; ++sc) {
+            uint32_t rs[16], rp[16];
+            float pv[16];
+            tmem_ld16(tS + sc * 16, rs);
+            tmem_ld16(tP + sc * 16, rp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float2 m2 = *reinterpret_cast<const float2*>(m + sc * 16 + j);
+              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, m2.x) - l2);
+              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), scale2, m2.y) - l2);
+              float d0 = __uint_as_float(rp[j]), d1 = __uint_as_float(rp[j + 1]);
+              float q0 = p0, q1 = p1;
+              if (DROP) {
+                bool k0, k1;
+                keep2(x0 + sc * 16 + j, k0, k1);
+                if (!k0) kbits &= ~(1u << (sc * 16 + j));
+                if (!k1) kbits &= ~(2u << (sc * 16 + j));
+                q0 = k0 ? p0 * dc.inv_keep : 0.f; d0 = k0 ? d0 * dc.inv_keep : 0.f;
+                q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
+              }
+              pv[j] = q0; pv[j + 1] = q1;
+              pk[sc * 16 + j] = p0; pk[sc * 16 + j + 1] = p1;
+              part = fmaf(p0, d0, fmaf(p1, d1, part));
+            }
+            store_row16(pimg, trow, half * 32 + sc * 16, pv);
+          }
+          red[half * 128 + trow] = part;
+        }
+        team_bar(e);
+        if (wact) {
+          dl = red[trow] + red[128 + trow];
+#pragma unroll
+          for (int sc = 0; sc < 2; ++sc) {
+            uint32_t rp[16];
+            float dsv[16];
+            tmem_ld16(tP + sc * 16, rp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float d = __uint_as_float(rp[j]);
+              if (DROP) d = ((kbits >> (sc * 16 + j)) & 1u) ? d * dc.inv_keep : 0.f;
+              dsv[j] = pk[sc * 16 + j] * (d - dl);
+            }
+            store_row16(dsimg, trow, half * 32 + sc * 16, dsv);
+          }
         }
       }
       fence_async();
@@ -417,7 +504,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
         tc_before();
         fence_async();
         mbar_arrive(&dq_empty[c.qt]);
-        mbar_arrive(&d_empty[qs]);
+        if (!ONEBLK) mbar_arrive(&d_empty[qs]);
         team_bar(e);
         if (st_thread) {
           const int n0p = min(max(P.ql.rows0p - r0, 0), 128);
@@ -473,16 +560,19 @@ int attn_ws_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dc
   if (int r = virt(dk, HD, a.Lk, P.kl, 64, &M.dk0f, &M.dk0t, &M.dk1)) return r;
   if (int r = virt(dv, HD, a.Lk, P.kl, 64, &M.dv0f, &M.dv0t, &M.dv1)) return r;
   const int nkb = key_blocks(P.kl);
+  if (nkb > 1) { if (int r = virt(ctx, ldctx, a.Lq, P.ql, 128, &M.o0f, &M.o0t, &M.o1)) return r; }
+  else { M.o0f = M.g0f; M.o0t = M.g0t; M.o1 = M.g1; }
   const unsigned grid = (unsigned)std::min<int64_t>(P.items, sm_count());
-  if (a.drop.p > 0.f) {
-    auto kern = attn_ws_bwd_kernel<true>;
-    FCMF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::kSmem));
-    kern<<<grid, BW_THREADS, BwdSmem::kSmem, st>>>(M, P, nkb, (const bf16*)ctx, ldctx, lse);
-  } else {
-    auto kern = attn_ws_bwd_kernel<false>;
-    FCMF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::kSmem));
-    kern<<<grid, BW_THREADS, BwdSmem::kSmem, st>>>(M, P, nkb, (const bf16*)ctx, ldctx, lse);
+#define WS_BWD(DR, OB)                                                                                              \
+  {                                                                                                                 \
+    auto kern = attn_ws_bwd_kernel<DR, OB>;                                                                         \
+    FCMF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem<OB>::kSmem)); \
+    kern<<<grid, BW_THREADS, BwdSmem<OB>::kSmem, st>>>(M, P, nkb, (const bf16*)ctx, ldctx, lse);                    \
   }
+  const bool drop = a.drop.p > 0.f;
+  if (nkb == 1) { if (drop) WS_BWD(true, true) else WS_BWD(false, true) }
+  else { if (drop) WS_BWD(true, false) else WS_BWD(false, false) }
+#undef WS_BWD
   FCMF_LAUNCH_OK();
   return 0;
 }

@@ -112,6 +112,11 @@ int fcmf_dtanh(const void* dy, const void* y, void* out, int64_t n, int dtype, v
 
 /* dst(bf16 or f32) <- src(f32) with optional transpose of a [rows, cols] matrix (weight staging). */
 int fcmf_cast_matrix(const float* src, void* dst, int64_t rows, int64_t cols, int transpose, int dtype, void* stream);
+/* The same with a destination row stride ld_dst (elements) >= the destination's row length: stages a weight whose leading
+ * extent is not a multiple of 8 (the 250 002-row vocabulary projection of the IAOG decoder, mm_modeling.py:645) into a
+ * zero-padded buffer the tensor-core GEMM accepts; elements outside [rows, cols] are not written. */
+int fcmf_cast_matrix_ld(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld_dst, int transpose, int dtype,
+                        void* stream);
 int fcmf_cast_to_f32(const void* src, float* dst, int64_t n, int dtype, void* stream);
 
 /* ---- attention -------------------------------------------------------------------------------------- */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "fcmf_gather_sum_rows": [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, _vp],
     "fcmf_dtanh": [_vp, _vp, _vp, _i64, C.c_int, _vp],
     "fcmf_cast_matrix": [_vp, _vp, _i64, _i64, C.c_int, C.c_int, _vp],
+    "fcmf_cast_matrix_ld": [_vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, _vp],
     "fcmf_cast_to_f32": [_vp, _vp, _i64, C.c_int, _vp],
     "fcmf_set_attn_engine": [C.c_int],
     "fcmf_attn_fwd": [C.POINTER(AttnDesc), _vp, _i64, _vp, C.c_int, _vp],

@@ -319,7 +319,7 @@ __global__ void dtanh_kernel(const T* __restrict__ dy, const T* __restrict__ y, 
 }
 
 template <typename T>
-__global__ void cast_matrix_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int transpose) {
+__global__ void cast_matrix_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int transpose, int64_t ld) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -330,12 +330,12 @@ __global__ void cast_matrix_kernel(const float* __restrict__ src, T* __restrict_
   if (!transpose) {
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(int64_t)r * cols + c] = from_f<T>(tile[i][threadIdx.x]);
+      if (r < rows && c < cols) dst[(int64_t)r * ld + c] = from_f<T>(tile[i][threadIdx.x]);
     }
-  } else {                                              // dst is [cols, rows]
+  } else {                                              // dst is [cols, rows] with row stride ld
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
       const int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(int64_t)c * rows + r] = from_f<T>(tile[threadIdx.x][i]);
+      if (r < rows && c < cols) dst[(int64_t)c * ld + r] = from_f<T>(tile[threadIdx.x][i]);
     }
   }
 }
@@ -425,16 +425,23 @@ extern "C" int fcmf_dtanh(const void* dy, const void* y, void* out, int64_t n, i
   return 0;
 }
 
-extern "C" int fcmf_cast_matrix(const float* src, void* dst, int64_t rows, int64_t cols, int transpose, int dtype, void* stream) {
+extern "C" int fcmf_cast_matrix_ld(const float* src, void* dst, int64_t rows, int64_t cols, int64_t ld_dst, int transpose, int dtype,
+                                   void* stream) {
   FCMF_CHECK_ARG(rows >= 0 && cols >= 0 && rows < (1LL << 31) && cols < (1LL << 31), "cast_matrix: bad shape");
+  FCMF_CHECK_ARG(ld_dst >= (transpose ? rows : cols), "cast_matrix: ld_dst %lld is smaller than the destination's row length", (long long)ld_dst);
   if (rows * cols == 0) return 0;
+  FCMF_CHECK_ARG((rows + 31) / 32 <= 65535, "cast_matrix: more than 65535 x 32 rows");
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
   cudaStream_t st = as_stream(stream);
-  if (dtype == FCMF_BF16) cast_matrix_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, (int)rows, (int)cols, transpose);
-  else if (dtype == FCMF_F32) cast_matrix_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, (int)rows, (int)cols, transpose);
+  if (dtype == FCMF_BF16) cast_matrix_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, (int)rows, (int)cols, transpose, ld_dst);
+  else if (dtype == FCMF_F32) cast_matrix_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, (int)rows, (int)cols, transpose, ld_dst);
   else return fail(FCMF_ERR_ARG, "cast_matrix: bad dtype %d", dtype);
   FCMF_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int fcmf_cast_matrix(const float* src, void* dst, int64_t rows, int64_t cols, int transpose, int dtype, void* stream) {
+  return fcmf_cast_matrix_ld(src, dst, rows, cols, transpose ? rows : cols, transpose, dtype, stream);
 }
 
 extern "C" int fcmf_cast_to_f32(const void* src, float* dst, int64_t n, int dtype, void* stream) {

@@ -10,6 +10,7 @@ Gradients live directly inside the flat bucket buffers (param.grad is a view), s
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import Dict, Iterable, List, Sequence, Tuple
 
 import torch
@@ -23,6 +24,16 @@ BUCKET_ORDER: Sequence[Tuple[str, ...]] = (
     ("encoder.mm_attention.",),
     ("encoder.box_head.", "encoder.roimap2text.", "encoder.vismap2text."),
 )
+
+
+# IAOG pre-training (FCMFSeq2Seq, run_pretraining_fcmf.py:301-337): the decoder's gradients are final first (it runs last in
+# forward), upper blocks before lower ones; the tied embedding / vocabulary projection (768 MB in fp32) becomes final at the
+# very end of the decoder's backward and overlaps the whole fusion backward.
+SEQ2SEQ_BUCKET_ORDER: Sequence[Tuple[str, ...]] = (
+    tuple(f"decoder.blks.block{i}." for i in range(11, 5, -1)),
+    tuple(f"decoder.blks.block{i}." for i in range(5, -1, -1)),
+    ("decoder.",),
+) + tuple(BUCKET_ORDER[1:])
 
 
 def fusion_named_parameters(model: torch.nn.Module):
@@ -64,6 +75,7 @@ class BucketedGradReducer:
                 self._bucket_of[id(p)] = bi
                 p.register_post_accumulate_grad_hook(self._on_grad_ready)
             self.flat.append(flat)
+        self._sync = True
         self._reset_counts()
 
     # ---- per step ---------------------------------------------------------------------------------------------
@@ -77,9 +89,33 @@ class BucketedGradReducer:
             f.zero_()
         self._reset_counts()
 
+    @contextmanager
+    def no_sync(self):
+        """Gradient accumulation (the reference's --gradient_accumulation_steps, run_multimodal_fcmf.py:478-483): backward
+        passes inside this context only accumulate into the flat buckets; the all-reduce runs with the first backward
+        outside it (the last micro-batch), exactly as torch DDP's no_sync()."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
+
     def _on_grad_ready(self, p: torch.nn.Parameter):
         bi = self._bucket_of[id(p)]
+        flat, g = self.flat[bi], p.grad
+        lo = flat.data_ptr()
+        if g is None or not (lo <= g.data_ptr() < lo + flat.numel() * flat.element_size()):
+            raise RuntimeError(
+                "BucketedGradReducer: a parameter's .grad no longer lives in its flat bucket (optimizer.zero_grad() / "
+                "model.zero_grad() default to set_to_none=True, which detaches it): zero gradients with reducer.zero_grad() "
+                "or zero_grad(set_to_none=False)")
+        if not self._sync:
+            return                                                    # accumulation micro-batch: no collective
         self._pending[bi] -= 1
+        if self._pending[bi] < 0:
+            raise RuntimeError(
+                "BucketedGradReducer: a second backward() reached a bucket that was already reduced this step; call "
+                "reducer.zero_grad() once per optimizer step and run accumulation micro-batches under reducer.no_sync()")
         if self._pending[bi] == 0 and self.world > 1:
             self._launch(bi)
 

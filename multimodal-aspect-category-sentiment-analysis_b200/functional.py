@@ -312,6 +312,56 @@ def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tenso
     return _ClassifierCE.apply(pooled, wc, bc, labels, row_scale, drop)
 
 
+# ------------------------------------------------------------------------------------------------- vocabulary projection
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _VocabLinear(Function):
+    """logits = x @ W^T + b for an output width V that need not be a multiple of 8 (IAOG: V = 250 002): the weight is staged
+    with zero rows up to Vp = ceil8(V), so forward, input-gradient and weight-gradient GEMMs all take the tcgen05 engine
+    (N = Vp resp. K = Vp); the caller sees the [M, V] view of the [M, Vp] buffer."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], engine: int):
+        V, H = weight.shape
+        Vp = _pad8(V)
+        w = ops.cast_matrix_padded(weight, x.dtype, Vp)
+        b = None
+        if bias is not None:
+            b = torch.zeros((Vp,), dtype=torch.float32, device=x.device)
+            b[:V].copy_(bias)
+        y = ops.gemm_tn(x, w, b, EPI_NONE, engine=engine)                       # [M, Vp]; pad columns are exactly 0
+        ctx.engine, ctx.has_bias, ctx.V, ctx.Vp = engine, bias is not None, V, Vp
+        ctx.save_for_backward(x, weight)
+        return y[:, :V]
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, weight = ctx.saved_tensors
+        V, Vp, M = ctx.V, ctx.Vp, dy.shape[0]
+        if (Vp > V and dy.stride(1) == 1 and dy.stride(0) == Vp and
+                dy.untyped_storage().nbytes() >= (dy.storage_offset() + M * Vp) * dy.element_size()):
+            dyp = dy.as_strided((M, Vp), (Vp, 1), dy.storage_offset())          # our own vocab-CE gradient: zero-padded storage
+            dyp[:, V:].zero_()
+        elif Vp == V:
+            dyp = _c2(dy)
+        else:
+            dyp = torch.zeros((M, Vp), dtype=dy.dtype, device=dy.device)
+            dyp[:, :V].copy_(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt = ops.cast_matrix_padded(weight, x.dtype, Vp, transpose=True)    # [H, Vp]
+            dx = ops.gemm_tn(dyp, wt, None, EPI_NONE, engine=ctx.engine)
+        dw, db = ops.gemm_wgrad(dyp, x, want_bias=ctx.has_bias, engine=ctx.engine)
+        return dx, dw[:V], (db[:V] if db is not None else None), None
+
+
+def vocab_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], engine: int = ENGINE_AUTO) -> Tensor:
+    """x [M, H] @ weight[V, H]^T + bias -> [M, V] (a view with row stride ceil8(V)); IAOGDecoder.dense (mm_modeling.py:645, 662)."""
+    return _VocabLinear.apply(x, weight, bias, engine)
+
+
 # ------------------------------------------------------------------------------------------------- vocabulary loss
 class _VocabCE(Function):
     @staticmethod

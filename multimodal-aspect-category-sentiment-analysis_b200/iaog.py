@@ -180,7 +180,10 @@ class IAOGDecoder(nn.Module):
             self._attention_weights[0][i] = blk.attention1.attention_weights
             self._attention_weights[1][i] = blk.attention2.attention_weights
         B, T, H = X.shape
-        return Fn.linear(X.reshape(B * T, H), self.dense.weight, self.dense.bias).view(B, T, -1)
+        V = self.dense.weight.shape[0]
+        if X.is_cuda and X.dtype == torch.bfloat16:      # tensor-core path also for V % 8 != 0 (250 002): zero-padded weight rows
+            return Fn.vocab_linear(X.reshape(B * T, H), self.dense.weight, self.dense.bias).unflatten(0, (B, T))
+        return Fn.linear(X.reshape(B * T, H), self.dense.weight, self.dense.bias).view(B, T, V)
 
     @property
     def attention_weights(self):

@@ -10,16 +10,20 @@ from _util import pkg
 
 
 def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    return port
+    """A rendezvous FILE (no TCP port race between the probe and the workers' bind)."""
+    import tempfile
+    fd, path = tempfile.mkstemp(prefix="fcmf_gloo_")
+    os.close(fd)
+    os.unlink(path)
+    return path
+
+
+def _init(rank, world, port):
+    dist.init_process_group("gloo", init_method=f"file://{port}", rank=rank, world_size=world)
 
 
 def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _init(rank, world, port)
     ddp = pkg("ddp")
     torch.manual_seed(0)
     model = torch.nn.ModuleDict({"classifier": torch.nn.Linear(4, 3), "text_pooler": torch.nn.Linear(4, 4),
@@ -33,7 +37,7 @@ def _worker(rank, world, port, q):
         loss = model["classifier"](model["text_pooler"](x)).sum() + model["other"](x).sum() * (step + 1)
         loss.backward()
         red.finish()
-    q.put((rank, {n: p.grad.clone() for n, p in named}))
+    q.put((rank, {n: p.grad.detach().numpy().copy() for n, p in named}))       # by value: the worker may exit before the parent reads
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,7 +49,7 @@ def test_bucketed_reducer_averages_over_ranks():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=120) for _ in range(world))
+    got = {r: {n: torch.from_numpy(v) for n, v in g.items()} for r, g in (q.get(timeout=120) for _ in range(world))}
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -85,8 +89,7 @@ def _fcmf_step(model, batch, sl, per, A):
 
 
 def _fcmf_worker(rank, world, port, want_path, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _init(rank, world, port)
     import _standins
     _standins.install_plain(pkg)
     ddp = pkg("ddp")
@@ -127,3 +130,70 @@ def test_sharded_fcmf_step_gradients_equal_single_process(tmp_path):
         p.join(60)
         assert p.exitcode == 0
     assert sorted(got) == [0, 1] and max(got.values()) < 1e-5, got
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Misuse is loud, accumulation is supported: set_to_none zeroing detaches the buckets; a second backward
+# without no_sync() would reduce stale data.
+def _toy():
+    torch.manual_seed(0)
+    model = torch.nn.ModuleDict({"classifier": torch.nn.Linear(4, 3), "other": torch.nn.Linear(4, 2)})
+    return model, [(n, p) for n, p in model.named_parameters()]
+
+
+def test_reducer_raises_when_grads_are_detached_or_backward_runs_twice():
+    import pytest
+    ddp = pkg("ddp")
+    model, named = _toy()
+    red = ddp.BucketedGradReducer(named)
+    x = torch.ones(2, 4)
+    red.zero_grad()
+    (model["classifier"](x).sum() + model["other"](x).sum()).backward()
+    red.finish()
+    with pytest.raises(RuntimeError, match="already reduced"):
+        (model["classifier"](x).sum() + model["other"](x).sum()).backward()         # no zero_grad(), no no_sync()
+    model.zero_grad()                                                               # set_to_none=True: detaches .grad
+    red.zero_grad()
+    with pytest.raises(RuntimeError, match="no longer lives in its flat bucket"):
+        (model["classifier"](x).sum() + model["other"](x).sum()).backward()
+
+
+def _accum_worker(rank, world, port, q):
+    _init(rank, world, port)
+    ddp = pkg("ddp")
+    model, named = _toy()
+    red = ddp.BucketedGradReducer(named)
+    xs = [torch.full((2, 4), float(rank + 1 + 10 * k)) for k in range(3)]
+    red.zero_grad()
+    with red.no_sync():
+        for x in xs[:-1]:                                                           # accumulation micro-batches
+            (model["classifier"](x).sum() + model["other"](x).sum()).backward()
+    (model["classifier"](xs[-1]).sum() + model["other"](xs[-1]).sum()).backward()   # last micro-batch: reduces the sum
+    red.finish()
+    q.put((rank, {n: p.grad.detach().numpy().copy() for n, p in named}))       # by value: the worker may exit before the parent reads
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reducer_gradient_accumulation_under_no_sync():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {r: {n: torch.from_numpy(v) for n, v in g.items()} for r, g in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    model, named = _toy()
+    want = {n: torch.zeros_like(p) for n, p in named}
+    for rank in range(world):
+        model.zero_grad()
+        for k in range(3):
+            x = torch.full((2, 4), float(rank + 1 + 10 * k))
+            (model["classifier"](x).sum() + model["other"](x).sum()).backward()
+        for n, p in named:
+            want[n] += p.grad / world
+    for n in want:
+        assert torch.allclose(got[0][n], want[n], atol=1e-5) and torch.allclose(got[1][n], want[n], atol=1e-5), n

@@ -97,11 +97,14 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
   uint64_t* s_full = bars + 18;        // [2] S / dP of team e in TMEM
   uint64_t* pds_full = bars + 20;      // [2] P' / dS images of team e written
   uint64_t* pds_empty = bars + 22;     // [2] ... and consumed by B
-  uint64_t* dq_full = bars + 24;       // [2] dQ of query tile qt complete
-  uint64_t* dq_empty = bars + 26;      // [2]
-  uint64_t* dkv_full = bars + 28;      // dK / dV of the current key block complete
-  uint64_t* dkv_empty = bars + 29;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  // "complete" signals are PER TEAM: a team waits for its own barrier in strictly increasing phases. (One barrier per query
+  // tile / key block shared by alternating teams let a team that ran ahead test the parity of a phase two completions
+  // away -- indistinguishable from the one already complete.)
+  uint64_t* dq_full = bars + 24;       // [2] team e: dQ of the tile of its last-key-block iteration is complete
+  uint64_t* dq_empty = bars + 26;      // [2] per query tile: the dQ accumulator has been drained
+  uint64_t* dkv_full = bars + 28;      // [2] team e: dK / dV of the key block of its last-query-tile iteration are complete
+  uint64_t* dkv_empty = bars + 30;     // the dK / dV accumulators have been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qt = P.n_qt, stride = gridDim.x;
@@ -115,9 +118,9 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&pds_full[i], 256); mbar_init(&pds_empty[i], 1);
-      mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 256);
+      mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 256); mbar_init(&dkv_full[i], 1);
     }
-    mbar_init(dkv_full, 1); mbar_init(dkv_empty, 256);
+    mbar_init(dkv_empty, 256);
     fence_init();
     const CUtensorMap* mp = &M.q0f;
     for (int i = 0; i < (int)(sizeof(BwdMaps) / sizeof(CUtensorMap)); ++i) prefetch_map(mp + i);
@@ -244,8 +247,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
         for (int kk = 0; kk < ks_q; ++kk)                                      // dK_g += dS^T . Q_qt
           umma(tm + 448, sdesc_mn(dsimg + kk * 2048, TILE_B), sdesc(q + kk * 2048, 8192), idesc(64, 1, 1), (c.qt > 0 || kk > 0) ? 1u : 0u);
         commit(&pds_empty[e]);
-        if (c.qt == n_qt - 1) { commit(dkv_full); commit(&kv_empty[kb % KVS]); }
-        if (c.g == nkb - 1) { commit(&dq_full[c.qt]); commit(&qg_empty[tt % QGS]); }
+        if (c.qt == n_qt - 1) { commit(&dkv_full[e]); commit(&kv_empty[kb % KVS]); }
+        if (c.g == nkb - 1) { commit(&dq_full[e]); commit(&qg_empty[tt % QGS]); }
       };
       const long long t0 = clock64();
       long long last = t0;
@@ -257,8 +260,11 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
         else {
           __nanosleep(32);
 #ifndef FCMF_WS_NO_TRAP
-          if (clock64() - last > 6000000000LL) {
-            printf("fcmf attn_ws_bwd: MMA issuer stalled (block %d, A %d, B %d of %d)\n", (int)blockIdx.x, ca.n, cb.n, total);
+          if (clock64() - last > 9000000000LL) {                   // later than the bounded waits of the other roles: they name the barrier
+            const int e = cb.n & 1, u = cb.n >> 1, kb = cb.it * nkb + cb.g;
+            printf("fcmf attn_ws_bwd: MMA issuer stalled (block %d, A %d, B %d of %d; B waits: pds_full %d dkv_empty %d dq_empty %d)\n",
+                   (int)blockIdx.x, ca.n, cb.n, total, (int)mbar_test(&pds_full[e], u & 1),
+                   (int)(cb.qt != 0 || mbar_test(dkv_empty, (kb & 1) ^ 1)), (int)(cb.g != 0 || mbar_test(&dq_empty[cb.qt], (cb.it & 1) ^ 1)));
             __trap();
           }
 #endif
@@ -330,6 +336,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       return lr >= 0 ? lse[((int64_t)xp * P.heads + xh) * P.Lq + lr] * kLog2e : INFINITY;
     };
     float l2_next = ONEBLK ? load_l2(c) : 0.f;
+    uint32_t n_dkv = 0, n_dq = 0;                                  // epilogues this team has run: phases of its "complete" barriers
     while (c.item < P.items) {
       const int p = c.item / P.heads, h = c.item - p * P.heads;
       const int kb = c.it * nkb + c.g, tt = c.it * n_qt + c.qt, u = c.n >> 1;
@@ -463,7 +470,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
 
       if (c.qt == n_qt - 1) {
         // ---- dV_g / dK_g: lanes 0..63 = the keys of block g (quadrants 0, 1); staged in the P' image, then TMA stores
-        mbar_wait(dkv_full, kb & 1, 9);
+        mbar_wait(&dkv_full[e], n_dkv & 1, 9);
+        ++n_dkv;
         tc_after();
         if (quad < 2) {
           uint32_t rv[32], rk[32];
@@ -493,7 +501,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       }
       if (c.g == nkb - 1) {
         // ---- dQ_qt: staged in the dS image
-        mbar_wait(&dq_full[c.qt], c.it & 1, 10);
+        mbar_wait(&dq_full[e], n_dq & 1, 10);
+        ++n_dq;
         tc_after();
         if (wact) {
           uint32_t rq[32];

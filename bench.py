@@ -33,6 +33,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FCMF_BENCH_WORKLOAD", "fusion"), choices=["fusion", "iaog"],
+                    help="fusion: BASELINE configs[1] (the headline); iaog: configs[3], the FCMFSeq2Seq pre-training step "
+                         "(fusion encoder + 12-block IAOG decoder + 250 002-way projection + CE, target length 32)")
+    ap.add_argument("--vocab", type=int, default=250002)
+    ap.add_argument("--tgt-len", type=int, default=32)
     ap.add_argument("--rows", default=os.environ.get("FCMF_BENCH_ROWS", "full"), choices=["full", "live"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (samples)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
@@ -305,11 +310,158 @@ def start_watchdog(seconds: float) -> None:
         t.start()
 
 
+def main_iaog(args):
+    """BASELINE.json configs[3]: one IAOG pre-training step of FCMFSeq2Seq (run_pretraining_fcmf.py:301-337) per sample batch:
+    fusion encoder (one prompt per sample, all 15 fused rows feed the decoder) -> 12 decoder blocks (teacher forced, T = 32)
+    -> tied 250 002-way vocabulary projection -> CrossEntropyLoss(ignore_index=-100); forward + backward (+ the gradient
+    all-reduce of all 271 M non-text-encoder parameters when N > 1). The text encoder is stubbed by a leaf sequence_output,
+    exactly as in the fusion workload."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    pkg.build()
+    synth, ops, lib = pkg.synth, pkg.ops, importlib.import_module(PKG + "._lib")
+    ddp = importlib.import_module(PKG + ".ddp")
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.bfloat16
+    dims = synth.FusionDims(batch=args.batch, aspects=1, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
+    B, T, V, L, H = dims.batch, args.tgt_len, args.vocab, dims.seq_len, dims.hidden
+    torch.manual_seed(42)
+    model = pkg.FCMFSeq2Seq(V, T, None, dims.num_imgs, dims.num_roi, 0.7)
+
+    class StubText(torch.nn.Module):
+        def forward(self, input_ids, token_type_ids, attention_mask):
+            return input_ids, None, None
+    model.encoder.bert = StubText()
+    model = model.to(dev).train() if args.mode == "train" else model.to(dev).eval()
+    model.encoder.compute_dtype = dt
+    model.decoder.compute_dtype = dt
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    reducer = ddp.BucketedGradReducer(named, bucket_order=ddp.SEQ2SEQ_BUCKET_ORDER) if world > 1 else None
+
+    host = synth.make_batch(dims, seed=1234 + rank)
+    g = torch.Generator().manual_seed(4321 + rank)
+    dec_x = torch.randint(3, V, (B, T), generator=g)
+    labels = torch.roll(dec_x, -1, dims=1)
+    labels[:, -1] = -100                                            # iaog_dataset.py:94-96
+    pin = {"seq": host["sequence_output"][:, 0].to(dt).pin_memory(), "vis": host["visual_embeds_att"].to(dt).pin_memory(),
+           "roi": host["roi_embeds_att"].to(dt).pin_memory(), "coors": host["roi_coors"].pin_memory(),
+           "mask": host["added_attention_mask"][:, 0].contiguous().pin_memory(), "attn": torch.ones(B, L, dtype=torch.int64).pin_memory(),
+           "dec_x": dec_x.pin_memory(), "labels": labels.pin_memory()}
+    res = {k: v.to(dev) for k, v in pin.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pin.values())
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            for p in model.parameters():
+                p.grad = None
+        seq = inp["seq"].detach().requires_grad_(True)
+        logits = model(seq, inp["dec_x"], inp["vis"], inp["roi"], inp["coors"], None, inp["attn"], inp["mask"], None, True)
+        loss = model.loss(logits, inp["labels"])
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    dev_in = {k: torch.empty_like(v) for k, v in res.items()}
+
+    def e2e_step():
+        for k, v in pin.items():
+            dev_in[k].copy_(v, non_blocking=True)
+        loss_host.copy_(step(dev_in).detach(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (lib.kernel_launches() - l0) // max(steps, 1)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.GEMM_PROFILE = []
+    ms, launches = timed(lambda: step(res), args.steps, args.warmup)
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(e2e_step, max(3, min(args.steps, 10)), 2)
+    if rank != 0:
+        leave(world, dist, torch)
+        return
+    per_step = len(prof) // (args.steps + args.warmup)
+    timed_entries = prof[-args.steps * per_step:] if prof else []
+    Vp = (V + 7) // 8 * 8
+    vocab = [(M, N, K, a.elapsed_time(b)) for (_, M, N, K, a, b) in timed_entries if Vp in (M, N, K)]
+    v_flops = sum(2.0 * M * N * K for (M, N, K, _) in vocab)
+    v_ms = sum(t for (*_, t) in vocab)
+    all_flops = sum(2.0 * M * N * K for (_, M, N, K, _, _) in timed_entries)
+    all_ms = sum(a.elapsed_time(b) for (*_, a, b) in timed_entries)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1590.0))
+    ach = v_flops / (v_ms * 1e-3) / 1e12 if v_ms > 0 else 0.0
+    n = world
+    line = {
+        "metric": "fcmf_iaog_seq2seq_fwd_bwd_samples_per_sec", "value": n * B / (ms * 1e-3), "unit": UNIT, "n_gpus": n,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[3]: IAOG Seq2Seq pre-training step (FCMF fusion encoder + 12-block IAOG decoder, "
+                               f"teacher-forced, target length {T}, vocabulary {V}), per-GPU batch {B}, L={L}, {dims.num_imgs} images x 49 "
+                               f"grid tokens, {dims.num_roi} ROIs/image, H={H}; text encoder stubbed by sequence_output",
+                   "global_batch": n * B, "parallelism": f"dp{n}", "mode": args.mode + ", random-init weights",
+                   "l2": "logits + weights per step (> 2 GB) exceed the 126 MB L2; no explicit flush",
+                   "step": "forward + backward" + (" + bucketed NCCL all-reduce of all non-text-encoder gradients overlapped with backward" if n > 1 else "")},
+        "clocks": clocks,
+        "e2e": {"value": n * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel on the vocabulary projection (forward, input gradient, weight gradient; "
+                                                   f"V padded {V} -> {Vp} with zero weight rows)",
+                     "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)",
+                     "traffic": None, "vocab_gemm_ms_per_step": v_ms / max(args.steps, 1), "vocab_gemm_launches_per_step": len(vocab) // max(args.steps, 1),
+                     "all_gemm_tflops": all_flops / (all_ms * 1e-3) / 1e12 if all_ms else None, "all_gemm_ms_per_step": all_ms / max(args.steps, 1)},
+        "cpu_baseline": None,
+        "grad_allreduce_bytes": reducer.message_bytes() if reducer is not None else 0,
+    }
+    print(json.dumps(line), flush=True)
+    leave(world, dist, torch)
+
+
 def main():
     args = parse()
     start_watchdog(args.max_seconds)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "iaog":
+        return main_iaog(args)
 
     import torch
     import torch.distributed as dist

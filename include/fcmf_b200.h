@@ -71,6 +71,12 @@ int fcmf_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const f
                  void* D, int64_t ldd, void* aux, int64_t ldaux,
                  int64_t M, int64_t N, int64_t K, int epi, int dtype, int engine, void* stream);
 
+/* D(fp32)[M,N] = A[M,K] . B[N,K]^T, bf16 operands, the reduction split across CTAs (fp32 atomics; D is zeroed by the call).
+ * For contractions with a small output and a long reduction: the input gradient of IAOGDecoder.dense (mm_modeling.py:645),
+ * [B*T, H] over K = vocabulary. tcgen05 engine only (FCMF_ERR_UNSUPPORTED otherwise). */
+int fcmf_gemm_tn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N,
+                     int64_t K, int dtype, void* stream);
+
 /* dW[N,K] (+)= dY[M,N]^T . X[M,K] ; db[N] (+)= column sums of dY (db may be NULL).  fp32 outputs.
  * Replaces autograd's weight/bias gradient of every nn.Linear above. */
 int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, float* db,

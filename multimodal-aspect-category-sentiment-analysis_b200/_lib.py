@@ -47,6 +47,7 @@ PROTOTYPES = {
     "fcmf_dropout_keep": [_f32, C.c_uint64, C.c_uint64, C.c_uint32],
     "fcmf_device_info": [C.POINTER(C.c_int)] * 3,
     "fcmf_gemm_tn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
+    "fcmf_gemm_tn_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, C.c_int, _vp],
     "fcmf_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int, C.c_int, _vp],
     "fcmf_gemm_wgrad_plan": [_i64, _i64, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)],
     "fcmf_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f32, C.POINTER(Dropout), C.c_int, _vp],

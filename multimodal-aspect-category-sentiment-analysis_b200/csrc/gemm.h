@@ -21,6 +21,8 @@ int gemm_tc_tn(const void* A, int64_t lda, const void* B, int64_t ldb, const flo
 int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t M, int64_t N,
                   int64_t K, int accumulate, cudaStream_t st);
 
+int gemm_tc_tn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N,
+                   int64_t K, cudaStream_t st);
 void gemm_tc_wgrad_plan(int64_t M, int64_t N, int64_t K, int* pair, int* tiles, int* splits, int* workers);
 
 }  // namespace fcmf

@@ -225,6 +225,16 @@ extern "C" int fcmf_gemm_tn(const void* A, int64_t lda, const void* B, int64_t l
   return gemm_simt_tn(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, dtype, st);
 }
 
+extern "C" int fcmf_gemm_tn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int64_t M,
+                                int64_t N, int64_t K, int dtype, void* stream) {
+  FCMF_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_tn_f32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  FCMF_CHECK_ARG(lda >= K && ldb >= K && ldd >= N, "gemm_tn_f32: leading dimension too small");
+  if (M == 0 || N == 0) return 0;
+  if (dtype != FCMF_BF16 || !gemm_tc_supported_tn(M, N, K, lda, ldb, 8, 0, A, B, nullptr, nullptr) || (reinterpret_cast<uintptr_t>(D) & 15u))
+    return fail(FCMF_ERR_UNSUPPORTED, "gemm_tn_f32: needs bf16 operands with 16-byte aligned rows (tcgen05 engine only)");
+  return gemm_tc_tn_f32(A, lda, B, ldb, D, ldd, M, N, K, as_stream(stream));
+}
+
 extern "C" int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, float* db,
                                int64_t M, int64_t N, int64_t K, int accumulate, int dtype, int engine, void* stream) {
   FCMF_CHECK_ARG(M >= 0 && N > 0 && K > 0, "gemm_wgrad: bad shape");

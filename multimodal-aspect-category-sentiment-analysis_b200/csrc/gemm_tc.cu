@@ -813,6 +813,39 @@ int gemm_tc_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, floa
   return bn == 256 ? launch<256, true, true>(m, P, st) : launch<128, true, true>(m, P, st);
 }
 
+// D(fp32)[M,N] = A[M,K] . B[N,K]^T with the reduction split over CTAs (fp32 atomics): for contractions whose output is small
+// and whose reduction is long -- the input gradient of the vocabulary projection, [2048 x 768] over K = 250 112: 24 output
+// tiles would occupy 24 of 74 CTA pairs.
+int gemm_tc_tn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int64_t M, int64_t N,
+                   int64_t K, cudaStream_t st) {
+  TcParams P{};
+  P.Mg = M; P.Ng = N; P.Kg = K;
+  P.k_blocks = (int)((K + TC_BK - 1) / TC_BK);
+  P.Df = D; P.lddf = ldd; P.epi = FCMF_EPI_NONE;
+  Maps m;
+  const bool two = use_2cta() && N % 256 == 0;
+  int bn = 256;
+  if (two) {
+    P.m_tiles = (int)((M + 255) / 256);
+    P.n_tiles = (int)(N / 256);
+    P.splits = pick_splits((int64_t)P.m_tiles * P.n_tiles, sm_count() / 2, P.k_blocks);
+    if (int r = make_map(&m.a, A, M, K, lda, TC_BK, 128)) return r;
+    if (int r = make_map(&m.b, B, N, K, ldb, TC_BK, 128)) return r;
+  } else {
+    bn = (N % 256 == 0) ? 256 : 128;
+    P.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    P.n_tiles = (int)((N + bn - 1) / bn);
+    P.splits = pick_splits((int64_t)P.m_tiles * P.n_tiles, sm_count(), P.k_blocks);
+    if (int r = make_map(&m.a, A, M, K, lda, TC_BK, TC_BM)) return r;
+    if (int r = make_map(&m.b, B, N, K, ldb, TC_BK, bn)) return r;
+  }
+  m.d = m.a; m.x = m.a;                                                  // unused in fp32 mode
+  P.f32_mode = P.splits == 1 ? 1 : 2;
+  if (P.f32_mode == 2) FCMF_CUDA_OK(cudaMemset2DAsync(D, sizeof(float) * ldd, 0, sizeof(float) * N, M, st));
+  if (two) return launch2<false, false>(m, P, st);
+  return bn == 256 ? launch<256, false, false>(m, P, st) : launch<128, false, false>(m, P, st);
+}
+
 // Tiling decision of gemm_tc_wgrad for a shape, without launching anything (host only): lets callers and the CPU
 // test-suite audit the wave efficiency of the split-K choice. workers = CTA pairs (2-CTA kernel) or CTAs.
 void gemm_tc_wgrad_plan(int64_t M, int64_t N, int64_t K, int* pair, int* tiles, int* splits, int* workers) {

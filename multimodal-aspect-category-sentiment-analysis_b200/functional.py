@@ -18,7 +18,7 @@ import torch
 from torch.autograd import Function
 
 from . import ops
-from ._lib import ENGINE_AUTO, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_TANH
+from ._lib import ENGINE_AUTO, ENGINE_SIMT, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_TANH
 
 Tensor = torch.Tensor
 
@@ -314,7 +314,8 @@ def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tenso
 
 # ------------------------------------------------------------------------------------------------- vocabulary projection
 def _pad8(n: int) -> int:
-    return (n + 7) // 8 * 8
+    """Padded width of a projection: a multiple of 8 (16-byte rows), of 256 when wide (whole CTA-pair tiles)."""
+    return (n + 7) // 8 * 8 if n <= 1024 else (n + 255) // 256 * 256
 
 
 class _VocabLinear(Function):
@@ -352,7 +353,10 @@ class _VocabLinear(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             wt = ops.cast_matrix_padded(weight, x.dtype, Vp, transpose=True)    # [H, Vp]
-            dx = ops.gemm_tn(dyp, wt, None, EPI_NONE, engine=ctx.engine)
+            if Vp >= 64 * x.shape[1] and x.dtype == torch.bfloat16 and ctx.engine != ENGINE_SIMT:
+                dx = ops.cast_matrix(ops.gemm_tn_f32(dyp, wt), x.dtype)        # small output, long reduction: split-K
+            else:
+                dx = ops.gemm_tn(dyp, wt, None, EPI_NONE, engine=ctx.engine)
         dw, db = ops.gemm_wgrad(dyp, x, want_bias=ctx.has_bias, engine=ctx.engine)
         return dx, dw[:V], (db[:V] if db is not None else None), None
 

@@ -82,3 +82,40 @@ def test_tc_matches_cuda_core_engine_bitwise_close():
     o1 = ops.gemm_tn(a, b, None, L.EPI_NONE, engine=L.ENGINE_TCGEN05)
     o2 = ops.gemm_tn(a, b, None, L.EPI_NONE, engine=L.ENGINE_SIMT)
     assert rel_err(o1, o2.float()) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(2048, 768, 25088), (300, 256, 20032), (130, 136, 8192), (64, 768, 640)])
+def test_tc_gemm_tn_f32_split_reduction(M, N, K):
+    """fp32 output with the reduction split across CTAs (the vocabulary projection's input gradient)."""
+    a, b = rnd(M, K, scale=0.1), rnd(N, K, scale=0.1, seed=3)
+    ref = a.float() @ b.float().t()
+    out = ops.gemm_tn_f32(a, b)
+    assert out.dtype == torch.float32 and rel_err(out, ref) < 2e-3
+
+
+def test_vocab_linear_padded_projection_fwd_bwd():
+    """V % 8 != 0 and wide (padded to a multiple of 256): forward, split-K input gradient, weight / bias gradients."""
+    Fn = pkg("functional")
+    M, H, V = 96, 64, 5003
+    x = rnd(M, H).requires_grad_(True)
+    w = (torch.randn(V, H, device="cuda") * 0.05).requires_grad_(True)
+    b = (torch.randn(V, device="cuda") * 0.1).requires_grad_(True)
+    y = Fn.vocab_linear(x, w, b)
+    assert y.shape == (M, V) and y.stride(0) % 256 == 0
+    xr, wr, br = x.detach().float().requires_grad_(True), w.detach().to(BF).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = xr @ wr.t() + br
+    assert rel_err(y, yr) < 1e-2
+    g = rnd(M, V, scale=0.1, seed=5)
+    y.backward(g)
+    yr.backward(g.float())
+    assert rel_err(x.grad, xr.grad) < 1e-2 and rel_err(w.grad, wr.grad) < 1e-2 and rel_err(b.grad, br.grad) < 1e-2
+    # through the vocabulary softmax-CE kernels (the gradient keeps the padded storage: no copy in backward)
+    labels = torch.randint(0, V, (M,), device="cuda")
+    x.grad = None; w.grad = None
+    loss = Fn.vocab_cross_entropy(Fn.vocab_linear(x, w, b), labels)
+    loss.backward()
+    xr.grad = None; wr.grad = None
+    lr = torch.nn.functional.cross_entropy(xr @ wr.t() + br, labels)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 1e-2 * abs(lr.item())
+    assert rel_err(x.grad, xr.grad) < 2e-2 and rel_err(w.grad, wr.grad) < 2e-2

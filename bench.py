@@ -410,12 +410,45 @@ def main_iaog(args):
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(e2e_step, max(3, min(args.steps, 10)), 2)
+    # the same step as ONE CUDA graph: the eager step is CPU-launch-bound (~900 launches, most of them tiny decoder kernels)
+    graph = None
+    try:
+        graphed = importlib.import_module(PKG + ".graphed")
+        static = {k: v.clone() for k, v in res.items()}
+
+        def run(st):
+            seq = st["seq"].detach().requires_grad_(True)
+            logits = model(seq, st["dec_x"], st["vis"], st["roi"], st["coors"], None, st["attn"], st["mask"], None, True)
+            loss = model.loss(logits, st["labels"])
+            loss.backward()
+            return loss
+        gstep = graphed.GraphedStep(run, [p for _, p in named], static, training=model.training, reducer=reducer)
+        ms_g, _ = timed(lambda: gstep(), max(5, args.steps) * 2, 3)
+
+        def e2e_graph():
+            gstep(pin)
+            loss_host.copy_(gstep.out.detach(), non_blocking=True)
+        ms_ge, _ = timed(e2e_graph, max(5, args.steps), 2)
+        graph = {"value": world * B / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "launches_per_replay": int(launches),
+                 "e2e": {"value": world * B / (ms_ge * 1e-3), "unit": UNIT, "ms_per_step": ms_ge,
+                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4}}
+    except Exception as e:                                       # capture is an optimisation, never a requirement
+        graph = {"unavailable": repr(e)[:300]}
     if rank != 0:
         leave(world, dist, torch)
         return
     per_step = len(prof) // (args.steps + args.warmup)
     timed_entries = prof[-args.steps * per_step:] if prof else []
-    Vp = (V + 7) // 8 * 8
+    Vp = (V + 7) // 8 * 8 if V <= 1024 else (V + 255) // 256 * 256        # functional._pad8
+    if os.environ.get("FCMF_BENCH_GEMM_TABLE"):
+        table = {}
+        for (kind, M, N, K, a, b) in timed_entries:
+            t = table.setdefault((kind, M, N, K), [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        for (kind, M, N, K), (cnt, t) in sorted(table.items(), key=lambda kv: -kv[1][1])[:24]:
+            print(f"  {kind:5s} M={M:7d} N={N:7d} K={K:7d} x{cnt // args.steps:3d}/step {t / cnt:8.3f} ms  "
+                  f"{2.0 * M * N * K / (t / cnt * 1e-3) / 1e12:7.1f} TFLOP/s", file=sys.stderr)
     vocab = [(M, N, K, a.elapsed_time(b)) for (_, M, N, K, a, b) in timed_entries if Vp in (M, N, K)]
     v_flops = sum(2.0 * M * N * K for (M, N, K, _) in vocab)
     v_ms = sum(t for (*_, t) in vocab)
@@ -448,7 +481,7 @@ def main_iaog(args):
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)",
                      "traffic": None, "vocab_gemm_ms_per_step": v_ms / max(args.steps, 1), "vocab_gemm_launches_per_step": len(vocab) // max(args.steps, 1),
                      "all_gemm_tflops": all_flops / (all_ms * 1e-3) / 1e12 if all_ms else None, "all_gemm_ms_per_step": all_ms / max(args.steps, 1)},
-        "cpu_baseline": None,
+        "cpu_baseline": None, "graph_replay": graph,
         "grad_allreduce_bytes": reducer.message_bytes() if reducer is not None else 0,
     }
     print(json.dumps(line), flush=True)

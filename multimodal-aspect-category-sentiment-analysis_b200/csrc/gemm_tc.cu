@@ -187,8 +187,14 @@ __device__ __forceinline__ void epilogue_f32(const TcParams& P, int64_t m, int64
   float* dp = P.Df + m * P.lddf + n0;
   const int ncols = (int)min((int64_t)32, P.Ng - n0);
   if (P.f32_mode == 1) {
+    if (ncols == 32 && (P.lddf & 3) == 0) {                      // 8 x 16-byte stores (the thread's 128 contiguous bytes)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(dp + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < ncols) dp[j] = __uint_as_float(r[j]);
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(dp + j, __uint_as_float(r[j]));
@@ -778,7 +784,10 @@ static int pick_splits(int64_t tiles, int64_t workers, int k_blocks) {
     if (s > 1 && (int64_t)(s - 1) * ((k_blocks + s - 1) / s) >= k_blocks) continue;      // would leave an empty split
     const int64_t units = tiles * s;
     const int64_t waves = (units + workers - 1) / workers;
-    const double eff = (double)units / (double)(waves * workers) - 0.004 * s;           // small cost per extra atomic pass
+    // every split adds one fp32-atomic epilogue pass over the tile (~60 k-blocks' worth of time): negligible against the
+    // 7 000-block reductions of the fusion path, dominant for a short reduction with a huge output (the vocabulary
+    // projection's weight gradient: 32 blocks, 768 MB of output -- three splits ran at 190 TFLOP/s behind their atomics)
+    const double eff = (double)units / (double)(waves * workers) / (1.0 + 60.0 * s / (double)k_blocks);
     if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
   }
   return best;

@@ -87,3 +87,65 @@ class GraphedFusionStep:
                     self.static[k].detach().copy_(v, non_blocking=True)
         self.graph.replay()
         return self.logits, self.loss
+
+
+class GraphedStep:
+    """CUDA-graph capture of an arbitrary fixed-shape training step built on this library's Functions (e.g. the IAOG
+    pre-training step: ~900 launches of mostly tiny decoder kernels, CPU-launch-bound when issued eagerly).
+
+        step = GraphedStep(run, params, static_inputs, training=model.training, reducer=None)
+        out = step(new_inputs)          # copies into the static buffers, replays, returns run()'s static outputs
+
+    ``run(static_inputs)`` performs forward + backward (NOT the gradient zeroing, NOT reducer.finish()) and returns a tensor or
+    tuple of tensors; gradients accumulate into static ``param.grad`` buffers that are zeroed in place inside the graph."""
+
+    def __init__(self, run, params, static_inputs: Dict[str, Tensor], training: bool, reducer=None, warmup: int = 3):
+        self.run, self.reducer = run, reducer
+        self.params = [p for p in params if p.requires_grad]
+        self.static = static_inputs
+        dev = next(iter(static_inputs.values())).device
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev) if training else None
+        Fn.set_seed_device_tensor(self.seed_dev)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._zero()
+                    self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if reducer is None:
+                for p in self.params:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                if self.seed_dev is not None:
+                    self.seed_dev.add_(1)
+                self._zero()
+                self.out = self._step()
+        finally:
+            Fn.set_seed_device_tensor(None)
+
+    def _zero(self):
+        if self.reducer is not None:
+            self.reducer.zero_grad()
+        else:
+            for p in self.params:
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    def _step(self):
+        out = self.run(self.static)
+        if self.reducer is not None:
+            self.reducer.finish()
+        return out
+
+    def __call__(self, inputs: Optional[Dict[str, Tensor]] = None):
+        if inputs is not None:
+            for k, v in inputs.items():
+                if v is not self.static[k]:
+                    self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -157,7 +157,14 @@ def test_weight_gradient_split_k_fills_the_last_wave():
         assert lib.fcmf_gemm_wgrad_plan(M, N, K, ctypes.byref(pair), ctypes.byref(tiles), ctypes.byref(splits), ctypes.byref(workers)) == 0
         units = tiles.value * splits.value
         waves = -(-units // workers.value)
-        assert 1 <= splits.value <= 32 and units / (waves * workers.value) >= 0.8, (M, N, K, tiles.value, splits.value)
+        assert 1 <= splits.value <= 32
+        if M >= 5000:      # long reductions: a split's extra atomic pass is noise, the last wave's fill is what counts
+            assert units / (waves * workers.value) >= 0.8, (M, N, K, tiles.value, splits.value)
+    # short reduction, huge output (the vocabulary projection's weight gradient, 32 k-blocks, 768 MB of fp32): never split --
+    # three splits measured 190 TFLOP/s behind their atomics
+    pair, tiles, splits, workers = i32(), i32(), i32(), i32()
+    assert lib.fcmf_gemm_wgrad_plan(2048, 250112, 768, ctypes.byref(pair), ctypes.byref(tiles), ctypes.byref(splits), ctypes.byref(workers)) == 0
+    assert splits.value == 1 and tiles.value == 2931
     assert lib.fcmf_gemm_wgrad_plan(0, 1, 1, None, None, None, None) != 0
 
 

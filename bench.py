@@ -283,19 +283,37 @@ def run_reference(args):
         "gpu_launches": 0}), flush=True)
 
 
-def leave(world, dist, torch):
-    """End of a multi-rank run. One 2-GPU run of this script printed its JSON line and then never exited: the teardown of
-    the NCCL communicator (whose collectives are also captured inside a live CUDA graph) blocked. The measurement is over
-    at this point, so: a last barrier (nobody is still inside a collective that reads a peer's memory), flush, and leave
-    without running the communicator / graph destructors."""
+def leave(world, dist, torch, graphs=()):
+    """End of a multi-rank run: an ORDERLY teardown. Round 1 left with os._exit because a 2-GPU run printed its line and then
+    never exited; the cause was destruction order -- a live CUDA graph still held the captured NCCL all-reduce nodes of the
+    communicator while interpreter shutdown destroyed the process group first. Now: drop the graphs (their captured
+    collectives with them), drain the device, barrier, destroy the process group. A short watchdog stays as a guard so that
+    a teardown regression can never hang a GPU box (it reports itself on stderr)."""
     if world <= 1:
         return
+    import gc
+
+    def bark():
+        sys.stderr.write("bench.py: teardown did not finish in 30 s; leaving with os._exit (please report)\n")
+        sys.stderr.flush()
+        os._exit(0)
+    t = threading.Timer(30.0, bark)
+    t.daemon = True
+    t.start()
+    for g in graphs:
+        try:
+            g.graph.reset()
+        except Exception:
+            pass
+    del graphs
+    gc.collect()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
+    dist.destroy_process_group()
+    t.cancel()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -412,6 +430,7 @@ def main_iaog(args):
     ms_e2e, _ = timed(e2e_step, max(3, min(args.steps, 10)), 2)
     # the same step as ONE CUDA graph: the eager step is CPU-launch-bound (~900 launches, most of them tiny decoder kernels)
     graph = None
+    gstep = None
     try:
         graphed = importlib.import_module(PKG + ".graphed")
         static = {k: v.clone() for k, v in res.items()}
@@ -435,7 +454,7 @@ def main_iaog(args):
     except Exception as e:                                       # capture is an optimisation, never a requirement
         graph = {"unavailable": repr(e)[:300]}
     if rank != 0:
-        leave(world, dist, torch)
+        leave(world, dist, torch, [gstep] if gstep is not None else [])
         return
     per_step = len(prof) // (args.steps + args.warmup)
     timed_entries = prof[-args.steps * per_step:] if prof else []
@@ -485,7 +504,7 @@ def main_iaog(args):
         "grad_allreduce_bytes": reducer.message_bytes() if reducer is not None else 0,
     }
     print(json.dumps(line), flush=True)
-    leave(world, dist, torch)
+    leave(world, dist, torch, [gstep] if gstep is not None else [])
 
 
 def main():
@@ -672,6 +691,7 @@ def main():
 
     # ---- the other row mode beside the headline (both must be shown, each labelled) -------
     other = None
+    live_graphs = []
     if not args.no_second_mode:
         orows = "live" if args.rows == "full" else "full"
         ms_o, l_o = timed(lambda: step(res, orows), max(3, min(args.steps, 10)), 3)
@@ -683,6 +703,7 @@ def main():
             try:
                 graphed = importlib.import_module(PKG + ".graphed")
                 gstep = graphed.GraphedFusionStep(model, res, aspects=A, rows="live", reducer=reducer)
+                live_graphs.append(gstep)
                 ms_g, _ = timed(lambda: gstep(), max(3, min(args.steps, 10)) * 4, 3)
                 other["graph_replay"] = {"value": n_gpus * B / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
                                          "launches_per_replay": int(l_o)}
@@ -690,7 +711,7 @@ def main():
                 other["graph_replay"] = {"unavailable": repr(e)[:300]}
 
     if rank != 0:
-        leave(world, dist, torch)
+        leave(world, dist, torch, live_graphs)
         return
 
     cpu = None
@@ -729,7 +750,7 @@ def main():
         "executed_tflops": {"gemm_only": g_flops / max(args.steps, 1) / (ms * 1e-3) / 1e12},
     }
     print(json.dumps(line), flush=True)
-    leave(world, dist, torch)
+    leave(world, dist, torch, live_graphs)
 
 
 if __name__ == "__main__":

@@ -33,9 +33,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FCMF_BENCH_WORKLOAD", "fusion"), choices=["fusion", "iaog"],
+    ap.add_argument("--workload", default=os.environ.get("FCMF_BENCH_WORKLOAD", "fusion"), choices=["fusion", "iaog", "whole"],
                     help="fusion: BASELINE configs[1] (the headline); iaog: configs[3], the FCMFSeq2Seq pre-training step "
-                         "(fusion encoder + 12-block IAOG decoder + 250 002-way projection + CE, target length 32)")
+                         "(fusion encoder + 12-block IAOG decoder + 250 002-way projection + CE, target length 32); "
+                         "whole: the whole fine-tuning step -- XLM-R text encoder on the kernels + fusion + clip + AdamW")
     ap.add_argument("--vocab", type=int, default=250002)
     ap.add_argument("--tgt-len", type=int, default=32)
     ap.add_argument("--rows", default=os.environ.get("FCMF_BENCH_ROWS", "full"), choices=["full", "live"])
@@ -507,6 +508,138 @@ def main_iaog(args):
     leave(world, dist, torch, [gstep] if gstep is not None else [])
 
 
+def main_whole(args):
+    """The whole fine-tuning step of run_multimodal_fcmf.py:439-489 on the kernels (SURVEY.md section 8(f).2 and (f).4 added to the
+    hot path): XLM-R-base text encoder (random init, 12 layers, vocab 250 002) over the 6 aspect prompts of every sample,
+    fusion, loss, backward, clip_grad_norm_(1.0) + AdamW as three launches. Token ids in, logits + loss out."""
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    pkg.build()
+    synth, lib = pkg.synth, importlib.import_module(PKG + "._lib")
+    ddp = importlib.import_module(PKG + ".ddp")
+    optim = importlib.import_module(PKG + ".optim")
+    mm = importlib.import_module(PKG + ".fcmf_framework.mm_modeling")
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fusion path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from transformers import XLMRobertaConfig, XLMRobertaModel
+    dims = synth.FusionDims(batch=args.batch, hidden=args.hidden, heads=args.heads, inter=args.inter, seq_len=args.seq_len)
+    B, A, L = dims.batch, dims.aspects, dims.seq_len
+    mm.HIDDEN_SIZE, mm.NUM_ATTENTION_HEADS, mm.INTERMEDIATE_SIZE = dims.hidden, dims.heads, dims.inter
+    torch.manual_seed(42)
+    cfg = XLMRobertaConfig(vocab_size=args.vocab, hidden_size=dims.hidden, num_hidden_layers=12 if dims.hidden == 768 else 24,
+                           num_attention_heads=dims.heads, intermediate_size=dims.inter, max_position_embeddings=514,
+                           type_vocab_size=1, pad_token_id=1)
+    cfg._attn_implementation = "eager"
+    model = pkg.FCMF(None, num_labels=dims.num_labels, num_imgs=dims.num_imgs, num_roi=dims.num_roi)
+    model.load_state_dict(synth.make_params(dims, seed=42), strict=True)
+    model.encoder.bert = mm.FeatureExtractor(cell=XLMRobertaModel(cfg, add_pooling_layer=True))
+    model.encoder.bert.use_kernels = True
+    model.encoder.bert.compute_dtype = torch.bfloat16
+    model = model.to(dev).train() if args.mode == "train" else model.to(dev).eval()
+    model.encoder.compute_dtype = torch.bfloat16
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and "bert.cell.pooler" not in n]   # the pooler never gets a gradient
+    reducer = ddp.BucketedGradReducer(named) if world > 1 else None
+    no_decay = ("bias", "LayerNorm.weight")                      # the reference's parameter groups (run_multimodal_fcmf.py:249-289)
+    groups = [{"params": [p for n, p in named if not any(k in n for k in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in named if any(k in n for k in no_decay)], "weight_decay": 0.0}]
+    opt = optim.FusedAdamW(groups, lr=3e-5, max_grad_norm=1.0)
+
+    host = synth.make_batch(dims, seed=1234 + rank)
+    g = torch.Generator().manual_seed(99 + rank)
+    pin = {"ids": torch.randint(3, args.vocab, (B, A, L), generator=g).pin_memory(),
+           "tt": torch.zeros(B, A, L, dtype=torch.int64).pin_memory(), "am": torch.ones(B, A, L, dtype=torch.int64).pin_memory(),
+           "vis": host["visual_embeds_att"].to(torch.bfloat16).pin_memory(), "roi": host["roi_embeds_att"].to(torch.bfloat16).pin_memory(),
+           "coors": host["roi_coors"].pin_memory(), "mask": host["added_attention_mask"].pin_memory(), "labels": host["labels"].pin_memory()}
+    res = {k: v.to(dev) for k, v in pin.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pin.values())
+    out_host = torch.empty((B, A, dims.num_labels), dtype=torch.float32).pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            for _, p in named:
+                p.grad = None
+        logits, loss = model.forward_all_aspects(inp["ids"], inp["vis"], inp["roi"], inp["coors"], inp["tt"], inp["am"], inp["mask"],
+                                                 labels=inp["labels"])
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return logits, loss
+
+    dev_in = {k: torch.empty_like(v) for k, v in res.items()}
+
+    def e2e_step():
+        for k, v in pin.items():
+            dev_in[k].copy_(v, non_blocking=True)
+        logits, loss = step(dev_in)
+        out_host.copy_(logits.detach(), non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.kernel_launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (lib.kernel_launches() - l0) // max(steps, 1)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(lambda: step(res), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(e2e_step, max(3, min(args.steps, 10)), 2)
+    if rank != 0:
+        leave(world, dist, torch)
+        return
+    n = world
+    text_fwd = 12 * (8.0 * L * dims.hidden ** 2 + 4.0 * L * L * dims.hidden + 4.0 * L * dims.hidden * dims.inter) * A   # per sample
+    fl = 3.0 * (text_fwd + synth.flops_forward_per_sample(dims, "full"))
+    line = {
+        "metric": "fcmf_whole_step_samples_per_sec", "value": n * B / (ms * 1e-3), "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"whole FCMF fine-tuning step: XLM-R-base text encoder (random init) on {A} aspect prompts x L={L} per sample "
+                               f"+ fusion (configs[1] shapes) + clip_grad_norm_(1.0) + AdamW over {sum(p.numel() for _, p in named) / 1e6:.0f} M "
+                               f"parameters, per-GPU batch {B}", "global_batch": n * B, "parallelism": f"dp{n}", "mode": args.mode,
+                   "l2": "working set per step exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": n * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": out_host.numel() * 4 + 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "whole step (all kernels)", "achieved": fl * B / (ms * 1e-3) / 1e12, "peak": 1420.7,
+                     "unit": "TFLOP/s", "frac": fl * B / (ms * 1e-3) / 1e12 / 1420.7, "traffic": None,
+                     "note": "algorithmic FLOPs (text encoder 3 x fwd + fusion F_full x 3) / step time: a whole-step figure, not a kernel's"},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+    leave(world, dist, torch)
+
+
 def main():
     args = parse()
     start_watchdog(args.max_seconds)
@@ -514,6 +647,8 @@ def main():
         return run_reference(args)
     if args.workload == "iaog":
         return main_iaog(args)
+    if args.workload == "whole":
+        return main_whole(args)
 
     import torch
     import torch.distributed as dist

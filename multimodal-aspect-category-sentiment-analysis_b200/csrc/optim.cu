@@ -1,4 +1,4 @@
-// DRAFT (round-2 preparation, NOT validated on a GPU yet).
+// Optimizer tail kernels (GPU-validated in round 2: tests/test_gpu_optim.py).
 // Optimizer tail of the training step (reference run_multimodal_fcmf.py:483-489):
 //   torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0) ; optimizer.step() with torch.optim.AdamW over 4 parameter
 //   groups -- ~100 small tensors, one foreach pass each plus a host synchronisation for the norm.

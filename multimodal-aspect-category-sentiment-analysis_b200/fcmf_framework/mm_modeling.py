@@ -284,14 +284,25 @@ class BertPooler(nn.Module):
 
 
 class FeatureExtractor(nn.Module):
-    """Upstream text encoder, unchanged HF module (reference mm_modeling.py:433-446) -- out of the kernel scope."""
+    """Upstream text encoder (reference mm_modeling.py:433-446): the HF module is the parameter container (``cell``:
+    state_dict keys, checkpoint loading, resize_token_embeddings unchanged). ``use_kernels = True`` executes its encoder
+    layers and pooler on this library's kernels (``..xlmr``); attention probabilities are then
+    not materialised (third return value None). Default: the stock HF forward."""
 
-    def __init__(self, pretrained_path):
+    def __init__(self, pretrained_path=None, cell=None):
         super().__init__()
-        from transformers import AutoModel
-        self.cell = AutoModel.from_pretrained(pretrained_path, local_files_only=True, attn_implementation="eager")
+        if cell is None:
+            from transformers import AutoModel
+            cell = AutoModel.from_pretrained(pretrained_path, local_files_only=True, attn_implementation="eager")
+        self.cell = cell
+        self.use_kernels = False
+        self.compute_dtype = None
+        self.engine = 0
 
     def forward(self, input_ids, token_type_ids, attention_mask):
+        if self.use_kernels and input_ids.is_cuda:
+            from .. import xlmr
+            return xlmr.encode(self.cell, input_ids, token_type_ids, attention_mask, self.compute_dtype, self.engine, self.training)
         out = self.cell(input_ids=input_ids, token_type_ids=token_type_ids, attention_mask=attention_mask,
                         output_attentions=True)
         return out[0], out[1], out[2]

@@ -1,4 +1,4 @@
-"""DRAFT (round-2 preparation, NOT validated on a GPU yet): the optimizer tail of the reference's training step as three
+"""The optimizer tail of the reference's training step as three
 kernel launches: ``clip_grad_norm_(model.parameters(), 1.0)`` + ``torch.optim.AdamW.step()``
 over the 4 parameter groups (run_multimodal_fcmf.py:249-289, 483-489), with the gradient norm and the clip coefficient kept
 on the device (no ``.item()`` synchronisation per step).

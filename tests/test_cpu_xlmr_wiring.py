@@ -1,4 +1,4 @@
-"""DRAFT (round-2 preparation): the ORCHESTRATION of xlmr.KernelFeatureExtractor (weight concatenation, mask, eps, pooler,
+"""the ORCHESTRATION of xlmr.KernelFeatureExtractor (weight concatenation, mask, eps, pooler,
 plan columns) checked on the CPU by substituting plain-torch stand-ins with the kernel Functions' contracts; the kernels
 themselves are covered by the GPU suites. Result must equal the Hugging Face module it wraps."""
 import math

@@ -1,4 +1,4 @@
-"""DRAFT (round-2 preparation): clip_grad_norm_(1.0) + torch.optim.AdamW over the reference's 4 parameter groups against
+"""clip_grad_norm_(1.0) + torch.optim.AdamW over the reference's 4 parameter groups against
 the fused three-launch tail, several steps, fp32."""
 import pytest
 import torch

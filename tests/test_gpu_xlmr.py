@@ -1,4 +1,4 @@
-"""DRAFT (round-2 preparation): the kernel-backed XLM-R encoder against the stock Hugging Face module it wraps, same
+"""The kernel-backed XLM-R encoder against the stock Hugging Face module it wraps, same
 weights and inputs, eval() mode; fp32 (CUDA-core engines) at 1e-4 on states and gradients, bf16 at the bf16 bar."""
 import pytest
 import torch

@@ -1,4 +1,4 @@
-// DRAFT (round-2 preparation, NOT run yet): does a SWIZZLE_128B TMA load whose shared-memory destination is 128-byte but
+// Probe (run on B200 in round 2, result in profiles/r02a_tma_swizzle_probe.txt: ADDRESS based): does a SWIZZLE_128B TMA load whose shared-memory destination is 128-byte but
 // NOT 1024-byte aligned swizzle by the ABSOLUTE shared address (chunk ^ ((addr >> 7) & 7)) or relative to the box start?
 // The attention kernels want to TMA-load a second row segment (the 4 ROI rows) behind 170 text rows of the same tile, i.e.
 // at tile row 170 = byte offset 21760 = 128-aligned, not 1024-aligned. If the swizzle is address based (hypothesis A) the

@@ -106,7 +106,17 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {          // "lo
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
+// The effective seed goes through a 64-bit finaliser (splitmix64) first: seeds that differ in a few low bits -- a captured
+// CUDA graph advances the device counter by one per replay -- would otherwise give masks that are row permutations of
+// each other (rowseed(seed + n, r) == rowseed(seed, r ^ lo(seed) ^ lo(seed + n)) for the plain xor).
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
 __host__ __device__ __forceinline__ uint32_t drop_rowseed(uint64_t seed, uint64_t row) {
+  seed = splitmix64(seed);
   const uint32_t a = mix32((uint32_t)row ^ (uint32_t)seed);
   return mix32(a ^ ((uint32_t)(row >> 32) * 0x9E3779B9U + (uint32_t)(seed >> 32)));
 }

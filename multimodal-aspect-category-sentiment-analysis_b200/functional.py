@@ -12,6 +12,7 @@ Granularity follows the reference's module boundaries so that each Function repl
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -21,6 +22,7 @@ from . import ops
 from ._lib import ENGINE_AUTO, ENGINE_SIMT, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_TANH
 
 Tensor = torch.Tensor
+_DEBUG = os.environ.get("FCMF_DEBUG", "0") not in ("", "0")     # host-side argument checks that cost a device synchronisation
 
 
 # ------------------------------------------------------------------------------------------------- dropout seeds
@@ -281,6 +283,10 @@ class _ClassifierCE(Function):
     @staticmethod
     def forward(ctx, pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float,
                 drop: Optional[ops.Drop]):
+        if labels is not None and _DEBUG:       # nn.CrossEntropyLoss raises on labels outside [0, C); the kernel ignores such rows
+            bad = (labels < 0) | (labels >= wc.shape[0])
+            if bool(bad.any()):
+                raise ValueError(f"classifier_ce: {int(bad.sum())} label(s) outside [0, {wc.shape[0]}) (checked because FCMF_DEBUG is set)")
         logits, probs, loss_rows = ops.cls_ce_fwd(pooled.contiguous(), wc.contiguous(), bc.contiguous(), labels, drop)
         ctx.row_scale, ctx.drop = row_scale, drop
         ctx.has_labels = labels is not None
@@ -308,6 +314,9 @@ class _ClassifierCE(Function):
 def classifier_ce(pooled: Tensor, wc: Tensor, bc: Tensor, labels: Optional[Tensor], row_scale: float = 1.0,
                   drop: Optional[ops.Drop] = None):
     """(logits [R,C] fp32, loss scalar = row_scale * sum_r CE(logits[r], labels[r])); labels=None -> logits only.
+    Labels outside [0, C) contribute 0 loss and 0 gradient (and the sum is still scaled by row_scale): the reference's labels
+    are always in range (vimacsa_dataset.py builds them from a 4-entry polarity map), where torch would raise; set
+    FCMF_DEBUG=1 to have them checked on the host (one synchronisation per call).
     drop: dropout on `pooled` before the classifier (fcmf_multimodal.py:49)."""
     return _ClassifierCE.apply(pooled, wc, bc, labels, row_scale, drop)
 

@@ -26,9 +26,16 @@ def mix32(x):
     return x
 
 
+def splitmix64(z: int) -> int:
+    z = (z + GOLDEN64) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
 def rowseed(seed: int, rows) -> np.ndarray:
     rows = np.asarray(rows, dtype=np.uint64)
-    seed &= M64
+    seed = splitmix64(seed & M64)
     lo, hi = np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32)
     a = mix32((rows & np.uint64(0xFFFFFFFF)).astype(np.uint32) ^ lo)
     with np.errstate(over="ignore"):

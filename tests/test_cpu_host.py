@@ -93,6 +93,11 @@ def test_dropout_mask_restatement_matches_the_library():
     a, b = big[:, 0::2], big[:, 1::2]                                                    # the two halves of a pair hash
     assert abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 5e-3
     assert abs(np.corrcoef(big[:-1].ravel(), big[1:].ravel())[0, 1]) < 5e-3              # adjacent rows
+    # consecutive seeds (CUDA-graph replays advance the device counter by one) give unrelated masks, not row permutations
+    m0, m1 = DM.keep_mask(777, np.arange(256), 768, 0.1), DM.keep_mask(778, np.arange(256), 768, 0.1)
+    rows0 = {r.tobytes() for r in m0}
+    assert sum(r.tobytes() in rows0 for r in m1) == 0
+    assert abs(np.corrcoef(m0.ravel(), m1.ravel())[0, 1]) < 1e-2
     thr, inv = DM.threshold(0.1)
     assert thr == 6554 and abs(inv - 1.0 / (1.0 - 6554 / 65536)) < 1e-6
 

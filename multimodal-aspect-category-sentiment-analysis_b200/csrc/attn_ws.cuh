@@ -222,10 +222,18 @@ static inline EncodeTiledFn encode_fn() {
   });
   return fn;
 }
+// The encode call is a DRIVER API: it needs a current context on the calling thread. A thread whose first CUDA work is one of
+// our calls (autograd's backward thread when an attention backward is the first op it runs) has none yet -> error 201.
+// One runtime call binds the primary context.
+static inline void bind_context() {
+  static thread_local bool bound = false;
+  if (!bound) { cudaFree(nullptr); bound = true; }
+}
 // 3-D bf16 tensor [groups][rows][cols] (row stride ld elements, group stride gstride elements); box = [64 cols][box_rows][1]
 static inline int make_map3(CUtensorMap* map, const void* ptr, int64_t cols, int64_t rows, int64_t groups, int64_t ld, int64_t gstride, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(FCMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  bind_context();
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)groups};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)gstride * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};

@@ -662,6 +662,10 @@ static EncodeTiledFn encode_fn() {
 static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(FCMF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  {   // driver API: the calling thread needs a current context (autograd's backward thread may not have one yet)
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(nullptr); bound = true; }
+  }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};

@@ -23,7 +23,7 @@ def case(heads, L1, L2, Lk1, p_drop, seed=0):
     p2ba, p2bi = (pidx // NI).contiguous(), ((pidx // (A * NI)) * NI + pidx % NI).contiguous()
     ba2p = (torch.arange(BA, device=dev, dtype=torch.int32).view(BA, 1) * NI + torch.arange(NI, device=dev, dtype=torch.int32)).contiguous()
     bi2p = torch.tensor([[(b * A + a) * NI + i for a in range(A)] for b in range(B) for i in range(NI)], device=dev, dtype=torch.int32)
-    tq = (torch.randn(BA * L1, 3 * HD, device=dev)).bfloat16().requires_grad_(True)
+    tq = (torch.randn(BA * L1, (HD if Lk1 else 3 * HD), device=dev)).bfloat16().requires_grad_(True)
     tensors = [tq]
     plan = Fn.AttnPlan(NP, heads, 64, mask_div=NI, drop=ops.Drop(p_drop, 1234) if p_drop > 0 else None)
     if Lk1:   # text -> image: q from the text tensor, k/v from a patch tensor indexed by (b, i)

@@ -225,6 +225,25 @@ extern "C" int fcmf_gemm_tn(const void* A, int64_t lda, const void* B, int64_t l
   return gemm_simt_tn(A, lda, B, ldb, bias, D, ldd, aux, ldaux, M, N, K, epi, dtype, st);
 }
 
+namespace {
+// one side stream + fork/join events per (thread, device): calls from different host threads never share them
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream* side_stream() {
+  static thread_local SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;            // never create objects while a capture is running
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { s.stream = nullptr; return nullptr; }
+    (void)cap;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return (s.stream && s.fork && s.join) ? &s : nullptr;
+}
+}  // namespace
+
 extern "C" int fcmf_gemm_tn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* D, int64_t ldd, int64_t M,
                                 int64_t N, int64_t K, int dtype, void* stream) {
   FCMF_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_tn_f32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
@@ -241,14 +260,30 @@ extern "C" int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int6
   FCMF_CHECK_ARG(dtype == FCMF_F32 || dtype == FCMF_BF16, "gemm_wgrad: bad dtype %d", dtype);
   FCMF_CHECK_ARG(lddy >= N && ldx >= K, "gemm_wgrad: leading dimension too small");
   cudaStream_t st = as_stream(stream);
-  if (db) { int r = colsum(dY, lddy, db, M, N, accumulate, dtype, st); if (r) return r; }
   const bool tc_ok = dtype == FCMF_BF16 && gemm_tc_supported_wgrad(M, N, K, lddy, ldx, dY, X);
   if (engine == FCMF_ENGINE_TCGEN05 && !tc_ok)
     return fail(FCMF_ERR_UNSUPPORTED, "gemm_wgrad: tcgen05 engine cannot run M=%lld N=%lld K=%lld dtype=%d",
                 (long long)M, (long long)N, (long long)K, dtype);
-  if (engine == FCMF_ENGINE_TCGEN05 || (engine == FCMF_ENGINE_AUTO && tc_ok))
-    return gemm_tc_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, st);
-  return gemm_simt_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, dtype, st);
+  const bool tc = engine == FCMF_ENGINE_TCGEN05 || (engine == FCMF_ENGINE_AUTO && tc_ok);
+  // The bias gradient (column sums of dY: an HBM-bound pass, 1.3 ms per config-2 step in total) runs on a side stream UNDER
+  // the tensor-bound weight-gradient GEMM of the same dY (fork / join with events; capturable into a CUDA graph).
+  SideStream* side = (db && tc && M >= 8192) ? side_stream() : nullptr;
+  if (db) {
+    if (side) {
+      FCMF_CUDA_OK(cudaEventRecord(side->fork, st));
+      FCMF_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      int r = colsum(dY, lddy, db, M, N, accumulate, dtype, side->stream);
+      if (r) return r;
+      FCMF_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    } else {
+      int r = colsum(dY, lddy, db, M, N, accumulate, dtype, st);
+      if (r) return r;
+    }
+  }
+  const int rc = tc ? gemm_tc_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, st)
+                    : gemm_simt_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, dtype, st);
+  if (side) FCMF_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  return rc;
 }
 
 // Host-only planning query: how the tcgen05 weight-gradient GEMM would tile and split this shape (no launch, no GPU needed).

@@ -268,21 +268,22 @@ extern "C" int fcmf_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int6
   // The bias gradient (column sums of dY: an HBM-bound pass, 1.3 ms per config-2 step in total) runs on a side stream UNDER
   // the tensor-bound weight-gradient GEMM of the same dY (fork / join with events; capturable into a CUDA graph).
   SideStream* side = (db && tc && M >= 8192) ? side_stream() : nullptr;
-  if (db) {
-    if (side) {
-      FCMF_CUDA_OK(cudaEventRecord(side->fork, st));
-      FCMF_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-      int r = colsum(dY, lddy, db, M, N, accumulate, dtype, side->stream);
-      if (r) return r;
-      FCMF_CUDA_OK(cudaEventRecord(side->join, side->stream));
-    } else {
-      int r = colsum(dY, lddy, db, M, N, accumulate, dtype, st);
-      if (r) return r;
-    }
+  if (db && !side) {
+    int r = colsum(dY, lddy, db, M, N, accumulate, dtype, st);
+    if (r) return r;
   }
+  if (side) FCMF_CUDA_OK(cudaEventRecord(side->fork, st));
+  // the GEMM is launched FIRST: its persistent CTAs (one per SM, ~200 KB of shared memory) become resident and the column-sum
+  // blocks fill what is left; launched the other way round the small blocks occupy the SMs and the GEMM CTAs wait for them
   const int rc = tc ? gemm_tc_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, st)
                     : gemm_simt_wgrad(dY, lddy, X, ldx, dW, M, N, K, accumulate, dtype, st);
-  if (side) FCMF_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  if (side) {
+    FCMF_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    int r = colsum(dY, lddy, db, M, N, accumulate, dtype, side->stream);
+    if (r) return r;
+    FCMF_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    FCMF_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  }
   return rc;
 }
 

@@ -824,9 +824,21 @@ def main():
                       "value": n_gpus * B / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m, "gpu_launches": l_m}
         model.train() if args.mode == "train" else model.eval()
 
+    # ---- the headline step replayed as ONE CUDA graph (same kernels, same inputs; reported beside the eager number) ------
+    live_graphs = []
+    head_graph = None
+    if not args.no_second_mode:
+        try:
+            graphed = importlib.import_module(PKG + ".graphed")
+            hstep = graphed.GraphedFusionStep(model, res, aspects=A, rows=args.rows, reducer=reducer)
+            live_graphs.append(hstep)
+            ms_h, _ = timed(lambda: hstep(), max(3, min(args.steps, 10)), 3)
+            head_graph = {"value": n_gpus * B / (ms_h * 1e-3), "unit": UNIT, "ms_per_step": ms_h, "rows": args.rows, "mode": args.mode}
+        except Exception as e:
+            head_graph = {"unavailable": repr(e)[:300]}
+
     # ---- the other row mode beside the headline (both must be shown, each labelled) -------
     other = None
-    live_graphs = []
     if not args.no_second_mode:
         orows = "live" if args.rows == "full" else "full"
         ms_o, l_o = timed(lambda: step(res, orows), max(3, min(args.steps, 10)), 3)
@@ -880,7 +892,7 @@ def main():
                    "step": "fusion forward + backward" + (" + bucketed NCCL gradient all-reduce overlapped with backward" if n_gpus > 1 else "")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step), "roofline": roofline, "cpu_baseline": cpu,
-        "other_row_mode": other, "other_dropout_mode": other_mode, "reference_eager_gpu": eager,
+        "graph_replay": head_graph, "other_row_mode": other, "other_dropout_mode": other_mode, "reference_eager_gpu": eager,
         "flops_fwd_bwd_per_sample": fl,
         "executed_tflops": {"gemm_only": g_flops / max(args.steps, 1) / (ms * 1e-3) / 1e12},
     }

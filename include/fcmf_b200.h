@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FCMF_ABI_VERSION 3
+#define FCMF_ABI_VERSION 4
 
 enum { FCMF_F32 = 0, FCMF_BF16 = 1 };
 enum { FCMF_ERR_ARG = -1, FCMF_ERR_CUDA = -2, FCMF_ERR_UNSUPPORTED = -3 };
@@ -53,7 +53,7 @@ int fcmf_dropout_keep(float p, uint64_t seed, uint64_t row, uint32_t col);
 
 int fcmf_abi_version(void);
 /* sizeof / offsetof audit of the by-value structs (0 sizeof(fcmf_dropout), 1 .seed, 2 .seed_dev, 3 sizeof(fcmf_seg), 4 .idx,
- * 5 sizeof(fcmf_attn_desc), 6 .mask_add, 7 .bias, 8 .scale, 9 .causal, 10 .drop; -1 otherwise): lets a binding check its
+ * 5 sizeof(fcmf_attn_desc), 6 .mask_add, 7 .bias, 8 .scale, 9 .causal, 10 .drop, 11 .engine, 12 fcmf_seg.groups; -1 otherwise): lets a binding check its
  * mirror of the layouts against the compiled library. */
 int fcmf_abi_layout(int which);
 const char* fcmf_last_error(void);
@@ -151,9 +151,12 @@ typedef struct {
                            mm_modeling.py:115-124; applies to self- and cross-attention alike). CUDA-core engine only. */
   fcmf_dropout drop;    /* dropout on the probabilities AFTER the softmax (mm_modeling.py:213, 260; roi_modeling.py:42-43):
                            ctx = (keep * P / (1-p)) . V; mask element = keep(row (p*heads + h)*Lq + i, column j). */
+  int32_t engine;       /* attention engine of THIS call (FCMF_ENGINE_*); 0 = the process default (fcmf_set_attn_engine).
+                           Per-call so that concurrent host threads (the reference's nn.DataParallel fallback,
+                           run_multimodal_fcmf.py:241-244) never share a mutable switch. */
 } fcmf_attn_desc;
 
-/* Attention engine for subsequent calls: FCMF_ENGINE_AUTO (tcgen05 for bf16, head_dim 64, no bias, 16 <= L <= 320;
+/* DEFAULT attention engine of the process (used by calls whose descriptor says engine = 0): FCMF_ENGINE_AUTO (tcgen05 for bf16, head_dim 64, no bias, 16 <= L <= 320;
  * CUDA-core otherwise), FCMF_ENGINE_SIMT or FCMF_ENGINE_TCGEN05 (fail if unsupported). Process-wide. */
 int fcmf_set_attn_engine(int engine);
 int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, float* lse, int dtype, void* stream);

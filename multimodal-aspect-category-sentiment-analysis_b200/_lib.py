@@ -11,7 +11,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfcmf_b200.so")
 
-ABI_VERSION = 3               # FCMF_ABI_VERSION of include/fcmf_b200.h
+ABI_VERSION = 4               # FCMF_ABI_VERSION of include/fcmf_b200.h
 F32, BF16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_TANH, EPI_DGELU = 0, 1, 2, 3
@@ -37,7 +37,7 @@ class AttnDesc(C.Structure):
     _fields_ = [("q", Seg * 2), ("k", Seg * 2), ("v", Seg * 2),
                 ("mask_add", _vp), ("ld_mask", _i64), ("mask_div", _i32),
                 ("bias", _vp), ("NP", _i32), ("heads", _i32), ("dh", _i32), ("scale", _f32), ("causal", _i32),
-                ("drop", Dropout)]
+                ("drop", Dropout), ("engine", _i32)]
 
 
 # name -> argtypes (every entry point returns int); must list EVERY symbol include/fcmf_b200.h declares.

@@ -237,6 +237,7 @@ static int to_dev(const fcmf_attn_desc* d, AttnDev* o) {
   o->bias = d->bias;
   o->NP = d->NP; o->heads = d->heads; o->dh = d->dh; o->scale = d->scale; o->causal = d->causal ? 1 : 0;
   o->drop = d->drop;
+  o->engine = (d->engine >= FCMF_ENGINE_SIMT && d->engine <= FCMF_ENGINE_TCGEN05) ? d->engine : 0;
   FCMF_CHECK_ARG(drop_check(&d->drop) == 0, "attn: dropout p must be in [0, 1)");
   o->Lq = o->q[0].rows + o->q[1].rows;
   o->Lk = o->k[0].rows + o->k[1].rows;
@@ -269,7 +270,7 @@ extern "C" int fcmf_attn_fwd(const fcmf_attn_desc* d, void* ctx, int64_t ldctx, 
   FCMF_CHECK_ARG(dtype == FCMF_F32 || dtype == FCMF_BF16, "attn_fwd: bad dtype %d", dtype);
   if (a.NP == 0) return 0;
   {
-    const int eng = attn_engine();
+    const int eng = a.engine ? a.engine : attn_engine();
     const bool ok = dtype == FCMF_BF16 && attn_tc_supported(a, ldctx, ctx);
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_fwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
     if (ok && eng != FCMF_ENGINE_SIMT && attn_ws_enabled() && attn_ws_supported(a, ldctx, ctx)) return attn_ws_fwd(a, ctx, ldctx, lse, as_stream(stream));
@@ -300,7 +301,7 @@ extern "C" int fcmf_attn_bwd(const fcmf_attn_desc* d, const void* ctx, int64_t l
   if (a.NP == 0) return 0;
   cudaStream_t st = as_stream(stream);
   {
-    const int eng = attn_engine();
+    const int eng = a.engine ? a.engine : attn_engine();
     const bool ok = dtype == FCMF_BF16 && dbias == nullptr && attn_tc_supported(a, ldctx, ctx) && (lddctx % 8) == 0;
     if (eng == FCMF_ENGINE_TCGEN05 && !ok) return fail(FCMF_ERR_UNSUPPORTED, "attn_bwd: tcgen05 engine needs bf16, head_dim 64, no bias, 16 <= L <= 320");
     if (ok && eng != FCMF_ENGINE_SIMT && attn_ws_enabled() && attn_ws_bwd_supported(a, ldctx, ctx, lddctx) &&

@@ -12,6 +12,7 @@ struct AttnDev {
   int NP, heads, dh, Lq, Lk;
   int causal;             // key j > query i => score := -1e4 (masked_fill semantics of the IAOG decoder, mm_modeling.py:115-124)
   float scale;
+  int engine;             // engine of this call (0: process default)
   fcmf_dropout drop;      // dropout on the attention probabilities (mm_modeling.py:213, 260; roi_modeling.py:42-43); p == 0: off
 };
 

@@ -78,6 +78,8 @@ extern "C" int fcmf_abi_layout(int which) {
     case 8: return (int)offsetof(fcmf_attn_desc, scale);
     case 9: return (int)offsetof(fcmf_attn_desc, causal);
     case 10: return (int)offsetof(fcmf_attn_desc, drop);
+    case 11: return (int)offsetof(fcmf_attn_desc, engine);
+    case 12: return (int)offsetof(fcmf_seg, groups);
     default: return -1;
   }
 }

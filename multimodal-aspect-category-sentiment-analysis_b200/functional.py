@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -30,7 +31,12 @@ _DEBUG = os.environ.get("FCMF_DEBUG", "0") not in ("", "0")     # host-side argu
 # the forward and backward kernels regenerate (no mask tensor); the site seed is step_seed + site_id * an odd constant.
 # step seeds come from torch's CPU generator, so torch.manual_seed() makes a training run reproducible.
 _GOLDEN64 = 0x9E3779B97F4A7C15
-_SEED_DEV: Optional[Tensor] = None            # device int64 [1] added to every seed by the kernels (CUDA-graph replay)
+_TLS = threading.local()                      # .seed_dev: device int64 [1] added to every seed by the kernels (CUDA-graph replay);
+                                              # per host thread: the nn.DataParallel fallback runs one thread per GPU
+
+
+def _seed_dev() -> Optional[Tensor]:
+    return getattr(_TLS, "seed_dev", None)
 
 
 def new_step_seed() -> int:
@@ -45,19 +51,18 @@ def site_drop(step_seed: Optional[int], site: int, p: float) -> Optional[ops.Dro
     """Drop description of `site` for this step; None when dropout is off (eval mode: step_seed None, or p == 0)."""
     if step_seed is None or p <= 0.0:
         return None
-    return ops.Drop(p, site_seed(step_seed, site), _SEED_DEV)
+    return ops.Drop(p, site_seed(step_seed, site), _seed_dev())
 
 
 def fresh_drop(p: float, training: bool) -> Optional[ops.Drop]:
     """A site with its own fresh seed (module-level calls outside the folded path)."""
-    return ops.Drop(p, new_step_seed(), _SEED_DEV) if (training and p > 0.0) else None
+    return ops.Drop(p, new_step_seed(), _seed_dev()) if (training and p > 0.0) else None
 
 
 def set_seed_device_tensor(t: Optional[Tensor]) -> None:
     """Device int64 [1] that every dropout kernel adds to its seed; graphed.py bumps it inside the captured graph so
     that each replay draws new masks. None = off."""
-    global _SEED_DEV
-    _SEED_DEV = t
+    _TLS.seed_dev = t
 
 
 def _c2(t: Tensor) -> Tensor:
@@ -157,8 +162,9 @@ class AttnPlan:
     """Static description of one folded attention launch: which tensor/columns/rows feed each segment."""
 
     def __init__(self, NP: int, heads: int, dh: int, mask_div: int = 1, causal: bool = False,
-                 drop: Optional[ops.Drop] = None):
+                 drop: Optional[ops.Drop] = None, engine: int = ENGINE_AUTO):
         self.NP, self.heads, self.dh, self.mask_div, self.causal = NP, heads, dh, mask_div, causal
+        self.engine = engine                          # attention engine of this launch (0: the process default)
         self.drop = drop                              # dropout on the probabilities, mask row = (p*heads + h)*Lq + i
         self.roles = {"q": [], "k": [], "v": []}     # lists of (tensor_slot, col, rows, idx, inv)
 
@@ -180,7 +186,7 @@ def _desc(plan: AttnPlan, tensors: Sequence[Tensor], mask_add, bias):
     segs = {role: [ops.SegSpec(tensors[s], col, rows, idx) for (s, col, rows, idx, _) in plan.roles[role]]
             for role in ("q", "k", "v")}
     return ops.make_attn_desc(segs["q"], segs["k"], segs["v"], plan.NP, plan.heads, plan.dh,
-                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias, plan.causal, plan.drop)
+                              1.0 / math.sqrt(plan.dh), mask_add, plan.mask_div, bias, plan.causal, plan.drop, plan.engine)
 
 
 class _FoldedAttention(Function):

@@ -109,7 +109,7 @@ def test_ctypes_struct_layouts_match_the_compiled_library():
     lib = L.load()
     want = [ctypes.sizeof(L.Dropout), L.Dropout.seed.offset, L.Dropout.seed_dev.offset, ctypes.sizeof(L.Seg), L.Seg.idx.offset,
             ctypes.sizeof(L.AttnDesc), L.AttnDesc.mask_add.offset, L.AttnDesc.bias.offset, L.AttnDesc.scale.offset,
-            L.AttnDesc.causal.offset, L.AttnDesc.drop.offset]
+            L.AttnDesc.causal.offset, L.AttnDesc.drop.offset, L.AttnDesc.engine.offset, L.Seg.groups.offset]
     got = [lib.fcmf_abi_layout(i) for i in range(len(want))]
     assert got == want, (got, want)
     assert lib.fcmf_abi_layout(99) == -1

@@ -113,7 +113,7 @@ def _(x, res, gamma, beta, eps):
 @torch.library.custom_op(f"{NS}::layer_norm_residual_bwd", mutates_args=())
 def layer_norm_residual_bwd(dy: Tensor, x: Tensor, res: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     ds, dg, db = ops.ln_bwd(dy.contiguous(), None, x.contiguous(), res.contiguous(), None, gamma, mean, rstd)
-    return ds, dg, db
+    return ds, dg.clone(), db.clone()            # dg / db are rows of one buffer: custom-op outputs must not alias each other
 
 
 @layer_norm_residual_bwd.register_fake

@@ -196,6 +196,7 @@ attn_ws_fwd_kernel(const __grid_constant__ FwdMaps M, const Params P, bf16* __re
       mbar_wait(&s_full[w], (c.t >> 1) & 1, 7);
       tc_after();
       float mx = -INFINITY, sum = 0.f;
+      float2 sum2 = f2(0.f, 0.f);
       if (wact) {
 #pragma unroll 1
         for (int cc = 0; cc < NC; ++cc) {
@@ -205,8 +206,9 @@ attn_ws_fwd_kernel(const __grid_constant__ FwdMaps M, const Params P, bf16* __re
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(m + cc * 32 + j);
-            mx = fmaxf(mx, fmaxf(fmaxf(fmaf(__uint_as_float(r[j]), scale2, m4.x), fmaf(__uint_as_float(r[j + 1]), scale2, m4.y)),
-                                 fmaxf(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z), fmaf(__uint_as_float(r[j + 3]), scale2, m4.w))));
+            const float2 a = __ffma2_rn(u2f2(r[j], r[j + 1]), f2(scale2, scale2), f2(m4.x, m4.y));
+            const float2 b = __ffma2_rn(u2f2(r[j + 2], r[j + 3]), f2(scale2, scale2), f2(m4.z, m4.w));
+            mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y)));
           }
         }
       }
@@ -225,11 +227,10 @@ attn_ws_fwd_kernel(const __grid_constant__ FwdMaps M, const Params P, bf16* __re
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = *reinterpret_cast<const float4*>(m + cc * 32 + j);
-            v[j] = ex2_approx(fmaf(__uint_as_float(r[j]), scale2, m4.x) - mx);
-            v[j + 1] = ex2_approx(fmaf(__uint_as_float(r[j + 1]), scale2, m4.y) - mx);
-            v[j + 2] = ex2_approx(fmaf(__uint_as_float(r[j + 2]), scale2, m4.z) - mx);
-            v[j + 3] = ex2_approx(fmaf(__uint_as_float(r[j + 3]), scale2, m4.w) - mx);
-            sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+            const float2 a = __fadd2_rn(__ffma2_rn(u2f2(r[j], r[j + 1]), f2(scale2, scale2), f2(m4.x, m4.y)), f2(-mx, -mx));
+            const float2 b = __fadd2_rn(__ffma2_rn(u2f2(r[j + 2], r[j + 3]), f2(scale2, scale2), f2(m4.z, m4.w)), f2(-mx, -mx));
+            v[j] = ex2_approx(a.x); v[j + 1] = ex2_approx(a.y); v[j + 2] = ex2_approx(b.x); v[j + 3] = ex2_approx(b.y);
+            sum2 = __fadd2_rn(sum2, __fadd2_rn(f2(v[j], v[j + 1]), f2(v[j + 2], v[j + 3])));
           }
           if (DROP) {                                            // the denominator keeps the dropped terms
             if ((cc + 1) * 32 <= P.kl.rows0p) {                  // chunk inside segment 0: padded position == key index
@@ -250,6 +251,7 @@ attn_ws_fwd_kernel(const __grid_constant__ FwdMaps M, const Params P, bf16* __re
           }
           store_row32(p_blk(w, slot, cc >> 1), trow, (cc & 1) * 32, v);
         }
+        sum = sum2.x + sum2.y;
       }
       fence_async();                                             // P (generic proxy) -> the MMA (async proxy)
       tc_before();

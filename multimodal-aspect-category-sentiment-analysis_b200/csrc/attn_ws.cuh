@@ -186,6 +186,10 @@ __device__ __forceinline__ void stage_out32(uint8_t* tile, int r, int c0, const 
   }
 }
 
+// packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): the same fp32 operations, two per instruction
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 u2f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
 // ------------------------------------------------------------------------------------------- padded row layout
 // Segment 0 occupies padded positions [0, rows0), zero fill up to rows0p = round_up(rows0, 8); segment 1 occupies
 // [rows0p, rows0p + rows1). `total` = one past the last real position.

@@ -391,8 +391,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const float2 m2 = *reinterpret_cast<const float2*>(m + sc * 16 + j);
-              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, m2.x) - l2);
-              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), scale2, m2.y) - l2);
+              const float2 xe = __fadd2_rn(__ffma2_rn(u2f2(rs[j], rs[j + 1]), f2(scale2, scale2), m2), f2(-l2, -l2));
+              const float p0 = ex2_approx(xe.x), p1 = ex2_approx(xe.y);
               float d0 = __uint_as_float(rp[j]), d1 = __uint_as_float(rp[j + 1]);
               float q0 = p0, q1 = p1;
               if (DROP) {
@@ -402,7 +402,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
                 q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
               }
               pv[j] = q0; pv[j + 1] = q1;
-              dsv[j] = p0 * (d0 - dl); dsv[j + 1] = p1 * (d1 - dl);
+              const float2 ds2 = __fmul2_rn(f2(p0, p1), __fadd2_rn(f2(d0, d1), f2(-dl, -dl)));
+              dsv[j] = ds2.x; dsv[j + 1] = ds2.y;
             }
             store_row16(pimg, trow, half * 32 + sc * 16, pv);
             store_row16(dsimg, trow, half * 32 + sc * 16, dsv);
@@ -425,8 +426,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               const float2 m2 = *reinterpret_cast<const float2*>(m + sc * 16 + j);
-              const float p0 = ex2_approx(fmaf(__uint_as_float(rs[j]), scale2, m2.x) - l2);
-              const float p1 = ex2_approx(fmaf(__uint_as_float(rs[j + 1]), scale2, m2.y) - l2);
+              const float2 xe = __fadd2_rn(__ffma2_rn(u2f2(rs[j], rs[j + 1]), f2(scale2, scale2), m2), f2(-l2, -l2));
+              const float p0 = ex2_approx(xe.x), p1 = ex2_approx(xe.y);
               float d0 = __uint_as_float(rp[j]), d1 = __uint_as_float(rp[j + 1]);
               float q0 = p0, q1 = p1;
               if (DROP) {

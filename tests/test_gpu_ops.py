@@ -177,7 +177,8 @@ def attn_ref(qs, ks, vs, idxq, idxk, mask_add, mask_div, bias, heads, dh):
                                           (torch.bfloat16, L.ENGINE_TCGEN05)])
 @pytest.mark.parametrize("two_seg,use_bias,dh,heads,L1,L2", [
     (True, False, 64, 4, 9, 4), (False, True, 96, 8, 7, 0), (False, False, 64, 12, 7, 0),
-    (True, False, 64, 2, 170, 4), (False, False, 64, 3, 49, 0), (False, False, 64, 1, 200, 0), (True, False, 64, 2, 130, 30)])
+    (True, False, 64, 2, 170, 4), (False, False, 64, 3, 49, 0), (False, False, 64, 1, 200, 0), (True, False, 64, 2, 130, 30),
+    (False, False, 64, 2, 100, 0), (True, False, 64, 2, 90, 20), (False, False, 64, 2, 128, 0), (True, False, 64, 1, 32, 8)])
 def test_folded_attention_fwd_bwd(dtype, engine, two_seg, use_bias, dh, heads, L1, L2):
     if engine == L.ENGINE_TCGEN05 and (use_bias or dh != 64 or L1 + L2 < 16):
         pytest.skip("tcgen05 attention covers bf16, head_dim 64, no bias, L >= 16")

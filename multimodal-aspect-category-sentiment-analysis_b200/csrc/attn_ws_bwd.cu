@@ -285,7 +285,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
 #pragma unroll
           for (int i = 0; i < 2; ++i) {                              // in flight while the tiles land
             const int lrow = logical_row(P.ql, qt * 128 + t2 + i * 64);
-            l2v[i] = lrow >= 0 ? lse[((int64_t)p * P.heads + h) * P.Lq + lrow] * kLog2e : INFINITY;   // padded rows: P = exp2(. - inf) = 0
+            l2v[i] = lrow >= 0 ? lse[((int64_t)p * P.heads + h) * P.Lq + lrow] : INFINITY;   // raw (scaled at the store below: no wait here); padded rows: P = exp2(. - inf) = 0
           }
           mbar_wait(&d_empty[slot], ((tt / QGS) & 1) ^ 1, 3);
           mbar_wait(&qg_full[slot], (tt / QGS) & 1, 4);
@@ -308,7 +308,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
               }
             }
             dlt[slot * 256 + r] = part;                              // padded rows: O and dO are zero-filled
-            dlt[slot * 256 + 128 + r] = l2v[i];
+            dlt[slot * 256 + 128 + r] = l2v[i] * kLog2e;
           }
           mbar_arrive(&d_full[slot]);
         }
@@ -333,7 +333,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       if (x.item >= P.items) return INFINITY;
       const int lr = logical_row(P.ql, x.qt * 128 + trow);
       const int xp = x.item / P.heads, xh = x.item - xp * P.heads;
-      return lr >= 0 ? lse[((int64_t)xp * P.heads + xh) * P.Lq + lr] * kLog2e : INFINITY;
+      return lr >= 0 ? lse[((int64_t)xp * P.heads + xh) * P.Lq + lr] : INFINITY;      // RAW: scaling it here would wait for the load at once
     };
     float l2_next = ONEBLK ? load_l2(c) : 0.f;
     uint32_t n_dkv = 0, n_dq = 0;                                  // epilogues this team has run: phases of its "complete" barriers
@@ -345,7 +345,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
       const int lrow = logical_row(P.ql, r0 + trow);
       const int wlo = r0 + quad * 32, whi = wlo + 32;
       const bool wact = wlo < P.ql.rows0 || (P.ql.rows1 > 0 && wlo < P.ql.rows0p + P.ql.rows1 && whi > P.ql.rows0p);
-      float l2 = l2_next, dl = 0.f;
+      float l2 = l2_next * kLog2e, dl = 0.f;                      // the prefetched value is consumed one iteration after its load
       if (ONEBLK) {
         It cn = c;
         next(cn, nkb, n_qt, stride);

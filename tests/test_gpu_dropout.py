@@ -30,9 +30,9 @@ def mask_t(seed, rows, ncols, p):
 
 # ------------------------------------------------------------------------------------------- LayerNorm site
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("H,with_counter", [(768, False), (1024, True), (64, False)])
-def test_layernorm_hidden_dropout(dtype, H, with_counter):
-    M, R, p, seed = 257, 31, 0.1, 0x1234567887654321
+@pytest.mark.parametrize("H,with_counter,M", [(768, False, 257), (1024, True, 257), (64, False, 257), (768, True, 7001), (896, False, 2100)])
+def test_layernorm_hidden_dropout(dtype, H, with_counter, M):
+    R, p, seed = 31, 0.1, 0x1234567887654321
     x, res = rnd(M, H, dtype=dtype), rnd(R, H, dtype=dtype, seed=2)
     idx = (torch.arange(M, device=dev()) % R).to(torch.int32)
     w, b = (1 + 0.1 * rnd(H, seed=4)), 0.1 * rnd(H, seed=5)
@@ -52,9 +52,10 @@ def test_layernorm_hidden_dropout(dtype, H, with_counter):
     ds, dx, dg, db = ops.ln_bwd_drop(dy, dy2, x, res, idx, w, mean, rstd, drop)
     assert rel_err(dx, xs.grad) < TOL[dtype]
     assert rel_err(dg, wr.grad) < TOL[dtype] and rel_err(db, br.grad) < TOL[dtype]
-    inv = torch.full((R, (M + R - 1) // R), -1, dtype=torch.int32, device=dev())
-    for m in range(M):
-        inv[m % R, m // R] = m
+    inv = torch.full((R, (M + R - 1) // R), -1, dtype=torch.int32)
+    ar = torch.arange(M)
+    inv[ar % R, ar // R] = ar.to(torch.int32)
+    inv = inv.to(dev())
     assert rel_err(ops.gather_sum_rows(ds, inv, R, inv.shape[1]), rs.grad) < TOL[dtype]
     # exactly the dropped elements have a zero x-gradient
     assert torch.equal(dx.float() == 0, (keep == 0) | (ds.float() == 0))

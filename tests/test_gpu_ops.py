@@ -91,9 +91,11 @@ def ln_ref(s, w, b, eps=1e-12):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("H", [768, 1024, 64])
-def test_layernorm_fwd_bwd(dtype, H):
-    M, R = 257, 31
+@pytest.mark.parametrize("H,M", [(768, 257), (1024, 257), (64, 257), (320, 300), (896, 129), (768, 9001), (64, 40013)])
+def test_layernorm_fwd_bwd(dtype, H, M):
+    # H picks the warps-per-row instantiation (one 16-byte vector per lane; 896 leaves the last warp half empty); the large M
+    # make every group walk several rows (grid-stride loop, next-row prefetch, double-buffered exchange slots)
+    R = 31
     x, res = rnd(M, H, dtype=dtype), rnd(R, H, dtype=dtype, seed=2)
     idx = (torch.arange(M, device=dev()) % R).to(torch.int32)
     w, b = (1 + 0.1 * rnd(H, seed=4)), 0.1 * rnd(H, seed=5)
@@ -109,9 +111,10 @@ def test_layernorm_fwd_bwd(dtype, H):
     assert rel_err(ds, xs.grad) < TOL[dtype]
     assert rel_err(dg, wr.grad) < TOL[dtype] and rel_err(db, br.grad) < TOL[dtype]
     # residual gradient = rows of ds summed per residual row (what layer_tail does with res_inv)
-    inv = torch.full((R, (M + R - 1) // R), -1, dtype=torch.int32, device=dev())
-    for m in range(M):
-        inv[m % R, m // R] = m
+    inv = torch.full((R, (M + R - 1) // R), -1, dtype=torch.int32)
+    ar = torch.arange(M)
+    inv[ar % R, ar // R] = ar.to(torch.int32)
+    inv = inv.to(dev())
     dres = ops.gather_sum_rows(ds, inv, R, inv.shape[1])
     assert rel_err(dres, rs.grad) < TOL[dtype]
 
@@ -300,10 +303,11 @@ def test_vocab_cross_entropy_matches_torch(dtype, R, V):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_layernorm_bwd_compact_upstream_gradient(dtype):
+@pytest.mark.parametrize("problems", [6, 400])
+def test_layernorm_bwd_compact_upstream_gradient(dtype, problems):
     """dy_every: only rows 0, E, 2E, ... carry an upstream gradient (BertPooler keeps token 0 of each problem); the kernel
     takes the compact [M/E, H] gradient and must equal the dense call with zeros in the other rows."""
-    M, H, E = 6 * 29, 768, 29
+    M, H, E = problems * 29, 768, 29
     x, res = rnd(M, H, dtype=dtype), rnd(M, H, dtype=dtype, seed=2)
     w, b = (1 + 0.1 * rnd(H, seed=4)), 0.1 * rnd(H, seed=5)
     _, mean, rstd = ops.ln_fwd(x, res, None, w, b)

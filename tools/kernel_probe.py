@@ -27,6 +27,7 @@ def build():
     t = {}
     t["x"], t["w_hh"], t["w_ih"], t["w_hi"] = rnd(M, H), rnd(H, H, scale=.05), rnd(I, H, scale=.05), rnd(H, I, scale=.05)
     t["g"], t["pre"] = rnd(M, I), rnd(M, I)
+    t["dy"], t["dy2"] = rnd(M, H), rnd(M, H)          # distinct upstream gradients: the LayerNorm backward streams four tensors in the real step
     t["bias_h"], t["bias_i"] = torch.randn(H, device=dev) * .1, torch.randn(I, device=dev) * .1
     t["gamma"], t["beta"] = torch.ones(H, device=dev), torch.zeros(H, device=dev)
     ix = fusion._index(B, A, Lt, NI, NR, False, torch.device(dev))
@@ -51,7 +52,7 @@ def launches(t):
     def ln_f():
         out["ln"] = ops.ln_fwd(t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], t["beta"])
     yield "ln_fwd [456960,768] + gathered residual", 0, ln_f
-    yield "ln_bwd [456960,768]", 0, lambda: ops.ln_bwd(t["x"], t["x"], t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], out["ln"][1], out["ln"][2])
+    yield "ln_bwd [456960,768]", 0, lambda: ops.ln_bwd(t["dy"], t["dy2"], t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], out["ln"][1], out["ln"][2])
     nh, dh = 12, 64
     plan1 = Fn.AttnPlan(NP, nh, dh, mask_div=NI).add("q", 0, 0, Lt, ix.p2ba, ix.ba2p).add("k", 1, 0, P, ix.p2bi, ix.bi2p).add("v", 1, H, P, ix.p2bi, ix.bi2p)
     plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI)
@@ -77,7 +78,7 @@ def launches(t):
     def ln_fd():
         out["lnd"] = ops.ln_fwd(t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], t["beta"], drop=drop)
     yield "ln_fwd + dropout", 0, ln_fd
-    yield "ln_bwd + dropout (two outputs)", 0, lambda: ops.ln_bwd_drop(t["x"], t["x"], t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], out["lnd"][1], out["lnd"][2], drop)
+    yield "ln_bwd + dropout (two outputs)", 0, lambda: ops.ln_bwd_drop(t["dy"], t["dy2"], t["x"], t["seq"], ix.t2i_res_idx, t["gamma"], out["lnd"][1], out["lnd"][2], drop)
     plan1d = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop).add("q", 0, 0, Lt, ix.p2ba, ix.ba2p).add("k", 1, 0, P, ix.p2bi, ix.bi2p).add("v", 1, H, P, ix.p2bi, ix.bi2p)
     plan2d = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop)
     for role, col in (("q", 0), ("k", H), ("v", 2 * H)):

@@ -70,7 +70,16 @@ __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 // shared, completion on the slot's mbarrier) that one lane issues one to two rows AHEAD: what is in flight no longer
 // lives in registers. With register prefetch alone a warp could afford one row ahead of at most three operand streams
 // (168 registers, 12 warps per SM) and the backward streamed 3.1-3.6 TB/s; the ring keeps ~120 KB per SM in flight.
-constexpr int LN_SLOTS = 2;
+#ifndef FCMF_LN_SLOTS
+#define FCMF_LN_SLOTS 2
+#endif
+#ifndef FCMF_LN_BWD_BLOCKS
+#define FCMF_LN_BWD_BLOCKS 3
+#endif
+#ifndef FCMF_LN_FWD_BLOCKS
+#define FCMF_LN_FWD_BLOCKS 5
+#endif
+constexpr int LN_SLOTS = FCMF_LN_SLOTS;
 __device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ln_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(count));
@@ -107,7 +116,7 @@ __device__ __forceinline__ uint4 lds16(const void* p) { return *reinterpret_cast
 // DROP: the dense output x goes through dropout BEFORE the residual add (BertSelfOutput / BertOutput,
 // mm_modeling.py:278, 326): s = keep(row, col) * x / (1 - p) + res, mask regenerated from (seed, row, col).
 template <typename T, int VPL, bool DROP>
-__global__ void __launch_bounds__(LN_WARPS * 32, 5)
+__global__ void __launch_bounds__(LN_WARPS * 32, FCMF_LN_FWD_BLOCKS)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t* __restrict__ res_idx,
               const float* __restrict__ gamma, const float* __restrict__ beta, T* __restrict__ y,
               float* __restrict__ mean, float* __restrict__ rstd, int64_t M, int H, float eps, fcmf_dropout drop) {
@@ -237,7 +246,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
 // residual row (L2-resident: it is shared by the 7 image problems of a sample-aspect pair), mean / rstd and the residual index
 // of the row after the next are prefetched in registers.
 template <typename T, int VPL, bool DROP>
-__global__ void __launch_bounds__(LN_WARPS * 32, 4)
+__global__ void __launch_bounds__(LN_WARPS * 32, FCMF_LN_BWD_BLOCKS)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* __restrict__ x, const T* __restrict__ res,
               const int32_t* __restrict__ res_idx, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ ds, T* __restrict__ dx,

@@ -146,7 +146,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
     ln_bulk_g2s(my_ring + (size_t)slot * rowbytes, x + r * H, rowbytes, &my_bar[slot]);
   };
   uint4 nr[VPL];                                        // the gathered residual row (L2-resident) is prefetched in registers
-  int64_t idx_next = 0;
+  int32_t idx_raw = 0;                               // residual index of the NEXT row, kept raw: widening it here would wait for the load
   if (lane == 0) {
 #pragma unroll
     for (int sl = 0; sl < LN_SLOTS; ++sl) if (row + sl * stride < M) fill(sl, row + sl * stride);
@@ -159,7 +159,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
       if (c < H) nr[i] = ld16(res + ri * H + c);
     }
   }
-  if (res && row + stride < M) idx_next = res_idx ? (int64_t)res_idx[row + stride] : row + stride;
+  if (res && res_idx && row + stride < M) idx_raw = res_idx[row + stride];
   uint32_t it = 0;
   for (; row < M; row += stride, ++it) {
     const int slot = (int)(it % LN_SLOTS);
@@ -201,9 +201,9 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const int32_t*
 #pragma unroll
       for (int i = 0; i < VPL; ++i) {
         const int c = (i * 32 + lane) * N;
-        if (c < H) nr[i] = ld16(res + idx_next * H + c);
+        if (c < H) nr[i] = ld16(res + (res_idx ? (int64_t)idx_raw : nrow) * H + c);
       }
-      if (nrow + stride < M) idx_next = res_idx ? (int64_t)res_idx[nrow + stride] : nrow + stride;
+      if (res_idx && nrow + stride < M) idx_raw = res_idx[nrow + stride];
     }
     const float mu = warp_sum(sum2.x + sum2.y) * inv_h;
     const float2 nmu = bc2(-mu);
@@ -295,7 +295,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   uint4 nr[VPL];
   float mu_n = 0.f, rs_n = 0.f;
-  int64_t idx_next = 0;
+  int32_t idx_raw = 0;                               // residual index of the NEXT row, kept raw: widening it here would wait for the load
   auto request = [&](int64_t r, int64_t ri) {          // register-side prefetch: statistics and the gathered residual row
     mu_n = mean[r]; rs_n = rstd[r];
     if (res) {
@@ -311,7 +311,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
     for (int sl = 0; sl < LN_SLOTS; ++sl) if (row + sl * stride < M) fill(sl, row + sl * stride);
   }
   if (row < M) request(row, res ? (res_idx ? (int64_t)res_idx[row] : row) : 0);
-  if (res && row + stride < M) idx_next = res_idx ? (int64_t)res_idx[row + stride] : row + stride;
+  if (res && res_idx && row + stride < M) idx_raw = res_idx[row + stride];
   uint32_t it = 0;
   for (; row < M; row += stride, ++it) {
     const int slot = (int)(it % LN_SLOTS);
@@ -380,8 +380,8 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy_add, const T* _
     if (lane == 0 && row + LN_SLOTS * stride < M) fill(slot, row + LN_SLOTS * stride);
     const int64_t nrow = row + stride;
     if (nrow < M) {
-      request(nrow, idx_next);
-      if (res && nrow + stride < M) idx_next = res_idx ? (int64_t)res_idx[nrow + stride] : nrow + stride;
+      request(nrow, res_idx ? (int64_t)idx_raw : nrow);
+      if (res && res_idx && nrow + stride < M) idx_raw = res_idx[nrow + stride];
     }
     const float s1 = warp_sum(s1v.x + s1v.y) * inv_h;
     const float s2 = warp_sum(s2v.x + s2v.y) * inv_h;

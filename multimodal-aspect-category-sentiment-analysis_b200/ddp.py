@@ -17,12 +17,15 @@ import torch
 import torch.distributed as dist
 
 # Grad-ready order of the fusion path's backward.
+# Order in which backward finishes the gradients (fusion.fused_forward issues the hoisted projections right before their consumers):
+# classifier -> fusion layer + text+ROI branch + its hoisted Q/K/V (all mm_attention) -> ROI side (box head, roimap2text) ->
+# text->image FFN (~3 ms before the end) -> text->image attention projections and vismap2text (the very end).
 BUCKET_ORDER: Sequence[Tuple[str, ...]] = (
     ("classifier.", "text_pooler."),
-    ("encoder.text2img_pooler.", "encoder.text2roi_pooler."),
-    ("encoder.text2img_attention.",),
-    ("encoder.mm_attention.",),
-    ("encoder.box_head.", "encoder.roimap2text.", "encoder.vismap2text."),
+    ("encoder.text2roi_pooler.", "encoder.mm_attention."),
+    ("encoder.box_head.", "encoder.roimap2text."),
+    ("encoder.text2img_pooler.", "encoder.text2img_attention.layer.0.output.", "encoder.text2img_attention.layer.0.intermediate."),
+    ("encoder.text2img_attention.", "encoder.vismap2text."),
 )
 
 

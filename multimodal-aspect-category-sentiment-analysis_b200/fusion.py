@@ -148,24 +148,15 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     vis2 = visual_embeds_att[:, :NI].to(dt).reshape(B * NI * P, Dv)
     roi2 = roi_embeds_att[:, :NI].to(dt).reshape(B * NI * NR, Dv)
 
-    # ---- once per sample ------------------------------------------------------------------------------
-    mark("fusion: per-sample projections + box attention")
+    # ---- once per sample: what the text->image branch needs ---------------------------------------------
+    # Issue order = reverse of the order in which backward finishes the gradients (autograd runs nodes in reverse creation order):
+    # every hoisted projection, and every torch.cat of weights, is created right before the branch that consumes it, so that its
+    # weight gradients are final when that branch's backward ends and their all-reduce bucket can start under the remaining backward
+    # (at N = 8 the mm_attention and ROI-side buckets used to become final after the last kernel of the step).
+    mark("fusion: per-sample image projections")
     patches = Fn.linear(vis2, enc.vismap2text.weight, enc.vismap2text.bias, engine=engine)            # [B*NI*P, H]
     w_kv, b_kv = _cat_wb((t2i.attention.self.key, t2i.attention.self.value))
     kv_p = Fn.linear(patches, w_kv, b_kv, engine=engine)                                                # [B*NI*P, 2H]
-    roi_p = Fn.linear(roi2, enc.roimap2text.weight, enc.roimap2text.bias, engine=engine)              # [B*NI*NR, H]
-    box = enc.box_head
-    w_b, b_b = _cat_wb(box.linears[:3])
-    qkv_b = Fn.linear(roi_p, w_b, b_b, engine=engine)                                                   # [B*NI*NR, 3H]
-    wg_w = torch.cat([g.weight for g in box.WGs], 0)                                                    # [8, 64]
-    wg_b = torch.cat([g.bias for g in box.WGs], 0)                                                      # [8]
-    geo = Fn.box_geometry(roi_coors[:, :NI].reshape(B * NI, NR, 4), wg_w, wg_b)                         # [B*NI, 8, NR, NR]
-    dkb = H // box.h
-    plan_b = Fn.AttnPlan(B * NI, box.h, dkb, drop=drop("box_attn", box)).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
-        .add("v", 0, 2 * H, NR, None, None)
-    ctx_b = Fn.folded_attention(plan_b, (qkv_b,), None, geo)                                            # [B*NI*NR, H]
-    rel = Fn.linear(ctx_b, box.linears[3].weight, box.linears[3].bias, engine=engine)                   # relative_roi
-    w_mm, b_mm = _cat_wb((mm.attention.self.query, mm.attention.self.key, mm.attention.self.value))
 
     # ---- once per (sample, aspect) ----------------------------------------------------------------------
     mark("fusion: per-(sample, aspect) projections")
@@ -173,13 +164,8 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     if live:
         cls_rows = sequence_output.to(dt)[:, 0, :]                                                      # [BA, H] strided
         q_t = Fn.linear(cls_rows, tq.weight, tq.bias, engine=engine)                                    # [BA, H]
-        kv_t = Fn.linear(seq2, w_mm[H:], b_mm[H:], engine=engine)                                       # [BA*L, 2H]
-        q0_mm = Fn.linear(cls_rows, w_mm[:H], b_mm[:H], engine=engine)                                  # [BA, H]
-        kv_r = Fn.linear(rel, w_mm[H:], b_mm[H:], engine=engine)                                        # [B*NI*NR, 2H]
     else:
         q_t = Fn.linear(seq2, tq.weight, tq.bias, engine=engine)                                        # [BA*L, H]
-        qkv_t = Fn.linear(seq2, w_mm, b_mm, engine=engine)                                              # [BA*L, 3H]
-        qkv_r = Fn.linear(rel, w_mm, b_mm, engine=engine)                                               # [B*NI*NR, 3H]
     Lq = 1 if live else L
     NP = BA * NI
 
@@ -194,8 +180,31 @@ def fused_forward(enc, sequence_output: Tensor, visual_embeds_att: Tensor, roi_e
     h_img = Fn.linear(y1, enc.text2img_pooler.dense.weight, enc.text2img_pooler.dense.bias,
                       act="tanh", engine=engine)                                                        # [NP, H]
 
+    # ---- once per sample: ROI side (box attention -> relative_roi), then once per (sample, aspect): Q/K/V of the text rows --------
+    mark("fusion: per-sample ROI projections + box attention")
+    roi_p = Fn.linear(roi2, enc.roimap2text.weight, enc.roimap2text.bias, engine=engine)              # [B*NI*NR, H]
+    box = enc.box_head
+    w_b, b_b = _cat_wb(box.linears[:3])
+    qkv_b = Fn.linear(roi_p, w_b, b_b, engine=engine)                                                   # [B*NI*NR, 3H]
+    wg_w = torch.cat([g.weight for g in box.WGs], 0)                                                    # [8, 64]
+    wg_b = torch.cat([g.bias for g in box.WGs], 0)                                                      # [8]
+    geo = Fn.box_geometry(roi_coors[:, :NI].reshape(B * NI, NR, 4), wg_w, wg_b)                         # [B*NI, 8, NR, NR]
+    dkb = H // box.h
+    plan_b = Fn.AttnPlan(B * NI, box.h, dkb, drop=drop("box_attn", box)).add("q", 0, 0, NR, None, None).add("k", 0, H, NR, None, None) \
+        .add("v", 0, 2 * H, NR, None, None)
+    ctx_b = Fn.folded_attention(plan_b, (qkv_b,), None, geo)                                            # [B*NI*NR, H]
+    rel = Fn.linear(ctx_b, box.linears[3].weight, box.linears[3].bias, engine=engine)                   # relative_roi
+    w_mm, b_mm = _cat_wb((mm.attention.self.query, mm.attention.self.key, mm.attention.self.value))
+
     # ---- text + ROI branch ---------------------------------------------------------------------------------
     mark("fusion: text+ROI branch")
+    if live:
+        kv_t = Fn.linear(seq2, w_mm[H:], b_mm[H:], engine=engine)                                       # [BA*L, 2H]
+        q0_mm = Fn.linear(cls_rows, w_mm[:H], b_mm[:H], engine=engine)                                  # [BA, H]
+        kv_r = Fn.linear(rel, w_mm[H:], b_mm[H:], engine=engine)                                        # [B*NI*NR, 2H]
+    else:
+        qkv_t = Fn.linear(seq2, w_mm, b_mm, engine=engine)                                              # [BA*L, 3H]
+        qkv_r = Fn.linear(rel, w_mm, b_mm, engine=engine)                                               # [B*NI*NR, 3H]
     if live:
         plan2 = Fn.AttnPlan(NP, nh, dh, mask_div=NI, drop=drop("mm_attn", mm.attention.self)).add("q", 0, 0, 1, ix.p2ba, ix.ba2p) \
             .add("k", 1, 0, L, ix.p2ba, ix.ba2p).add("k", 2, 0, NR, ix.p2bi, ix.bi2p) \

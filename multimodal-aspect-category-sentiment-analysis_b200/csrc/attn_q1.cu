@@ -1,7 +1,7 @@
 // Single-query folded attention (Lq == 1): the "live rows" form of the fusion path, where only the [CLS] query of
 // every (sample, aspect, image) problem reaches an output (BertPooler keeps token 0, mm_modeling.py:425-431).
-// One warp = one (problem, head). No shared-memory staging of K/V (each key row is touched twice by one warp and
-// served by L1/L2); lanes map to KEYS for the score / dP dot products (16-byte row loads, q and dO broadcast from
+// One warp = one (problem, head); a block = consecutive problems of one head. No shared-memory staging of K/V (each key row is
+// touched twice by one warp and served by L1/L2); lanes map to KEYS for the score / dP dot products (16-byte row loads, q and dO broadcast from
 // shared memory) and to head DIMENSIONS for the P.V / dS.K accumulations and for every global store (coalesced
 // 128-byte rows). fp32 math, bf16 or fp32 storage, head_dim <= 128, Lk <= Q1_MAX_LK.
 #include "common.cuh"
@@ -32,9 +32,11 @@ attn_q1_fwd_kernel(AttnDev a, T* __restrict__ ctx, int64_t ldctx, float* __restr
   __shared__ float qs[Q1_WARPS][Q1_MAX_DH];
   __shared__ float ps[Q1_WARPS][Q1_MAX_LK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * Q1_WARPS + warp;
-  if (w >= (int64_t)a.NP * a.heads) return;
-  const int p = (int)(w / a.heads), h = (int)(w % a.heads);
+  // a block = Q1_WARPS CONSECUTIVE problems of ONE head: in the folded layout consecutive problems are the images of one (sample, aspect)
+  // and read the same text K/V rows, so the block's warps share them through L1 instead of each pulling them from L2
+  const int h = (int)(blockIdx.x % (unsigned)a.heads);
+  const int p = (int)(blockIdx.x / (unsigned)a.heads) * Q1_WARPS + warp;
+  if (p >= a.NP) return;
   const int dh = a.dh, Lk = a.Lk;
   float* q = qs[warp];
   float* pr = ps[warp];
@@ -78,9 +80,11 @@ attn_q1_bwd_kernel(AttnDev a, const T* __restrict__ ctx, int64_t ldctx, const T*
   __shared__ float qs[Q1_WARPS][2 * Q1_MAX_DH];      // q | dO
   __shared__ float ps[Q1_WARPS][2 * Q1_MAX_LK];      // P | dS
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * Q1_WARPS + warp;
-  if (w >= (int64_t)a.NP * a.heads) return;
-  const int p = (int)(w / a.heads), h = (int)(w % a.heads);
+  // a block = Q1_WARPS CONSECUTIVE problems of ONE head: in the folded layout consecutive problems are the images of one (sample, aspect)
+  // and read the same text K/V rows, so the block's warps share them through L1 instead of each pulling them from L2
+  const int h = (int)(blockIdx.x % (unsigned)a.heads);
+  const int p = (int)(blockIdx.x / (unsigned)a.heads) * Q1_WARPS + warp;
+  if (p >= a.NP) return;
   const int dh = a.dh, Lk = a.Lk, HD = a.heads * dh;
   float* q = qs[warp];
   float* go = q + Q1_MAX_DH;
@@ -146,8 +150,7 @@ bool attn_q1_supported(const AttnDev& a) {
 }
 
 int attn_q1_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, int dtype, cudaStream_t st) {
-  const int64_t warps = (int64_t)a.NP * a.heads;
-  const unsigned grid = (unsigned)((warps + Q1_WARPS - 1) / Q1_WARPS);
+  const unsigned grid = (unsigned)(((int64_t)a.NP + Q1_WARPS - 1) / Q1_WARPS * a.heads);
   if (dtype == FCMF_BF16) attn_q1_fwd_kernel<bf16><<<grid, Q1_WARPS * 32, 0, st>>>(a, (bf16*)ctx, ldctx, lse);
   else attn_q1_fwd_kernel<float><<<grid, Q1_WARPS * 32, 0, st>>>(a, (float*)ctx, ldctx, lse);
   FCMF_LAUNCH_OK();
@@ -156,8 +159,7 @@ int attn_q1_fwd(const AttnDev& a, void* ctx, int64_t ldctx, float* lse, int dtyp
 
 int attn_q1_bwd(const AttnDev& a, const void* ctx, int64_t ldctx, const void* dctx, int64_t lddctx, const float* lse,
                 void* dq, void* dk, void* dv, int dtype, cudaStream_t st) {
-  const int64_t warps = (int64_t)a.NP * a.heads;
-  const unsigned grid = (unsigned)((warps + Q1_WARPS - 1) / Q1_WARPS);
+  const unsigned grid = (unsigned)(((int64_t)a.NP + Q1_WARPS - 1) / Q1_WARPS * a.heads);
   if (dtype == FCMF_BF16)
     attn_q1_bwd_kernel<bf16><<<grid, Q1_WARPS * 32, 0, st>>>(a, (const bf16*)ctx, ldctx, (const bf16*)dctx, lddctx, lse,
                                                              (bf16*)dq, (bf16*)dk, (bf16*)dv);

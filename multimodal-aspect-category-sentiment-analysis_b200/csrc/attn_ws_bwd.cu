@@ -327,6 +327,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
     const int gap = P.kl.rows0p - P.kl.rows0;
     DropCfg dc;
     if (DROP) dc = make_drop(P.drop);
+    const float log2_inv_keep = DROP ? log2f(dc.inv_keep) : 0.f, keep_prob = DROP ? 1.0f / dc.inv_keep : 1.0f;
     It c{(int)blockIdx.x, 0, 0, 0, 0};
     if (e == 1) next(c, nkb, n_qt, stride);
     auto load_l2 = [&](const It& x) -> float {                        // ONEBLK: lse of this thread's row, prefetched one iteration ahead
@@ -358,6 +359,9 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
         dl = dlt[qs * 256 + trow];
         l2 = dlt[qs * 256 + 128 + trow];
       }
+      // train(): P carries the 1/(1-p) of the kept entries from the exponent (pI = P / (1 - p)), so the per-element products
+      // P' = keep * P / (1-p) and dP' = keep * dP / (1-p) become selects: dS = P (dP' - delta) = pI (keep * dP - delta (1-p))
+      if (DROP) { l2 -= log2_inv_keep; dl *= keep_prob; }
       mbar_wait(&s_full[e], u & 1, 7);
       tc_after();
       // P' / dS images of this team: consumed by B two iterations ago; staging reads of its TMA stores have finished
@@ -398,8 +402,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
               if (DROP) {
                 bool k0, k1;
                 keep2(x0 + sc * 16 + j, k0, k1);
-                q0 = k0 ? p0 * dc.inv_keep : 0.f; d0 = k0 ? d0 * dc.inv_keep : 0.f;
-                q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
+                q0 = k0 ? p0 : 0.f; d0 = k0 ? d0 : 0.f;
+                q1 = k1 ? p1 : 0.f; d1 = k1 ? d1 : 0.f;
               }
               pv[j] = q0; pv[j + 1] = q1;
               const float2 ds2 = __fmul2_rn(f2(p0, p1), __fadd2_rn(f2(d0, d1), f2(-dl, -dl)));
@@ -435,8 +439,8 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
                 keep2(x0 + sc * 16 + j, k0, k1);
                 if (!k0) kbits &= ~(1u << (sc * 16 + j));
                 if (!k1) kbits &= ~(2u << (sc * 16 + j));
-                q0 = k0 ? p0 * dc.inv_keep : 0.f; d0 = k0 ? d0 * dc.inv_keep : 0.f;
-                q1 = k1 ? p1 * dc.inv_keep : 0.f; d1 = k1 ? d1 * dc.inv_keep : 0.f;
+                q0 = k0 ? p0 : 0.f; d0 = k0 ? d0 : 0.f;
+                q1 = k1 ? p1 : 0.f; d1 = k1 ? d1 : 0.f;
               }
               pv[j] = q0; pv[j + 1] = q1;
               pk[sc * 16 + j] = p0; pk[sc * 16 + j + 1] = p1;
@@ -449,6 +453,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
         team_bar(e);
         if (wact) {
           dl = red[trow] + red[128 + trow];
+          if (DROP) dl *= keep_prob;
 #pragma unroll
           for (int sc = 0; sc < 2; ++sc) {
             uint32_t rp[16];
@@ -458,7 +463,7 @@ attn_ws_bwd_kernel(const __grid_constant__ BwdMaps M, const Params P, int nkb, c
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float d = __uint_as_float(rp[j]);
-              if (DROP) d = ((kbits >> (sc * 16 + j)) & 1u) ? d * dc.inv_keep : 0.f;
+              if (DROP) d = ((kbits >> (sc * 16 + j)) & 1u) ? d : 0.f;
               dsv[j] = pk[sc * 16 + j] * (d - dl);
             }
             store_row16(dsimg, trow, half * 32 + sc * 16, dsv);
